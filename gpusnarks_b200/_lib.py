@@ -1,0 +1,61 @@
+"""ctypes loader for libgpusnarks_b200.so.  Fails loudly: a missing library is an ImportError,
+a missing GPU is an error from gsn_ctx_create -- there is no CPU path behind this module."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgpusnarks_b200.so")
+
+# every symbol include/gpusnarks_b200.h declares (tests check that the .so exports them all)
+SYMBOLS = [
+    "gsn_ctx_create", "gsn_ctx_destroy", "gsn_last_error", "gsn_set_field768", "gsn_ctx_trim", "gsn_launch_count",
+    "gsn_ntt768_host", "gsn_ntt768_device", "gsn_ntt768_prepare", "gsn_ntt768_strided_device",
+    "gsn_fp768_twiddle_device", "gsn_fp768_binop_host", "gsn_ntt32_host", "gsn_ntt32_device",
+    "gsn_device_count", "gsn_host_alloc", "gsn_host_free", "gsn_device_alloc", "gsn_device_free",
+    "gsn_memcpy_h2d", "gsn_memcpy_d2h", "gsn_ctx_synchronize", "gsn_int32_issue_rates",
+    "gsn_ntt768_time_device", "gsn_ntt32_time_device",
+]
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m gpusnarks_b200.build` "
+            "(nvcc, sm_100a).  gpusnarks_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, u32p, sz, i, u32, u64p = C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.POINTER(C.c_uint64)
+    L.gsn_last_error.restype = C.c_char_p
+    L.gsn_ctx_create.argtypes = [C.POINTER(vp), i]
+    L.gsn_ctx_destroy.argtypes = [vp]
+    L.gsn_set_field768.argtypes = [vp, i]
+    L.gsn_ctx_trim.argtypes = [vp]
+    L.gsn_launch_count.argtypes = [vp, u64p]
+    L.gsn_ntt768_host.argtypes = [vp, u32p, sz, u32p, i]
+    L.gsn_ntt768_device.argtypes = [vp, vp, sz, sz, u32p, i, vp]
+    L.gsn_ntt768_prepare.argtypes = [vp, sz, sz, u32p, i]
+    L.gsn_ntt768_strided_device.argtypes = [vp, vp, sz, sz, C.c_uint, u32p, i, vp]
+    L.gsn_fp768_twiddle_device.argtypes = [vp, vp, sz, sz, sz, sz, sz, u32p, vp]
+    L.gsn_fp768_binop_host.argtypes = [vp, i, u32p, u32p, u32p, sz]
+    L.gsn_ntt32_host.argtypes = [vp, u32p, sz, u32, u32, i]
+    L.gsn_ntt32_device.argtypes = [vp, vp, sz, sz, u32, u32, i, vp]
+    L.gsn_device_count.argtypes = [C.POINTER(i)]
+    L.gsn_host_alloc.argtypes = [C.POINTER(vp), sz]
+    L.gsn_host_free.argtypes = [vp]
+    L.gsn_device_alloc.argtypes = [vp, C.POINTER(vp), sz]
+    L.gsn_device_free.argtypes = [vp, vp]
+    L.gsn_memcpy_h2d.argtypes = [vp, vp, vp, sz]
+    L.gsn_memcpy_d2h.argtypes = [vp, vp, vp, sz]
+    L.gsn_ctx_synchronize.argtypes = [vp]
+    L.gsn_int32_issue_rates.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i), C.POINTER(i)]
+    L.gsn_ntt768_time_device.argtypes = [vp, vp, sz, sz, u32p, i, i, C.POINTER(C.c_float)]
+    L.gsn_ntt32_time_device.argtypes = [vp, vp, sz, sz, u32, u32, i, i, i, C.POINTER(C.c_float)]
+    for s in SYMBOLS:
+        if s != "gsn_last_error":
+            getattr(L, s).restype = i
+    _lib = L
+    return L

@@ -1,0 +1,210 @@
+// fp768.cuh -- 768-bit (24 x 32-bit limb) Montgomery field arithmetic for sm_100a.
+//
+// Replaces the reference's device_field_operators.h (reference
+// cuda/device_field_operators.h:92-258: less/_add/_subtract/montyNormalize/
+// ciosMontgomeryMultiply/Scalar::add/subtract/mul) with PTX carry-chain code:
+//   * add.cc / addc.cc / sub.cc / subc.cc chains for add, sub and the conditional
+//     corrections (branch free, select by the borrow word);
+//   * a CIOS Montgomery product whose 2*24*24 word products are issued as
+//     mad.lo.cc / madc.hi.cc pairs on the same operands, which ptxas fuses into one
+//     IMAD.WIDE.U32 with a predicate carry.  To keep every 64-bit product on an
+//     aligned (even, odd) register pair the running sum is held in two interleaved
+//     accumulators: `ev` collects the products that start on an even limb of the
+//     current frame, `od` those that start on an odd limb.  Each outer iteration
+//     ends with a one-limb right shift (the Montgomery division by 2^32), which
+//     swaps the alignment of the two accumulators -- so the loop is unrolled by two
+//     with the roles exchanged, and no data ever moves.
+// Values are kept "lazy" in [0, 2p) between butterfly stages (p has 753 bits, the
+// container 768, so there are 15 bits of headroom) and are made canonical, [0, p),
+// only where they leave the transform.
+//
+// The modulus lives in __constant__ memory so that one binary serves MNT4-753 Fr
+// (default) and Fq (the reference's literal `_mod`); with fully unrolled loops every
+// modulus word is a constant-bank operand of the IMAD and costs no register.
+#pragma once
+#include <cstdint>
+
+namespace gsn {
+
+constexpr int NL = 24;  // reference: #define SIZE (768 / 32), cuda/device_field.h:35
+
+struct FieldConstants768 {
+    uint32_t p[NL];    // modulus
+    uint32_t p2[NL];   // 2 * modulus
+    uint32_t r1[NL];   // R mod p  (Montgomery one)
+    uint32_t r2[NL];   // R^2 mod p
+    uint32_t np0;      // -p^-1 mod 2^32
+    uint32_t pad[3];
+};
+
+__constant__ FieldConstants768 c_fp;
+
+// ------------------------------------------------------------------ carry-chain primitives
+__device__ __forceinline__ uint32_t add_cc(uint32_t a, uint32_t b) {
+    uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+}
+__device__ __forceinline__ uint32_t addc_cc(uint32_t a, uint32_t b) {
+    uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+}
+__device__ __forceinline__ uint32_t addc(uint32_t a, uint32_t b) {
+    uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+}
+__device__ __forceinline__ uint32_t sub_cc(uint32_t a, uint32_t b) {
+    uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+}
+__device__ __forceinline__ uint32_t subc_cc(uint32_t a, uint32_t b) {
+    uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+}
+__device__ __forceinline__ uint32_t subc(uint32_t a, uint32_t b) {
+    uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+}
+// (hi:lo) = a*b            (no carry in, no carry out)
+__device__ __forceinline__ void mul_wide(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b) {
+    asm volatile("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+}
+// (hi:lo) += a*b           starts a chain: carry out in CC
+__device__ __forceinline__ void mad_wide_cc(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b) {
+    asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+// (hi:lo) += a*b + CC      continues a chain
+__device__ __forceinline__ void madc_wide_cc(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b) {
+    asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+// (dhi:dlo) = (shi:slo) + a*b + CC   continues a chain, separate source pair (the shifted accumulate)
+__device__ __forceinline__ void madc_wide_cc_from(uint32_t &dlo, uint32_t &dhi, uint32_t a, uint32_t b, uint32_t slo, uint32_t shi) {
+    asm volatile("madc.lo.cc.u32 %0, %2, %3, %4; madc.hi.cc.u32 %1, %2, %3, %5;" : "=r"(dlo), "=r"(dhi) : "r"(a), "r"(b), "r"(slo), "r"(shi));
+}
+
+// ------------------------------------------------------------------ add / sub
+// r = a + b            (no reduction; caller guarantees no overflow of 768 bits)
+__device__ __forceinline__ void add_raw(uint32_t *r, const uint32_t *a, const uint32_t *b) {
+    r[0] = add_cc(a[0], b[0]);
+#pragma unroll
+    for (int i = 1; i < NL - 1; ++i) r[i] = addc_cc(a[i], b[i]);
+    r[NL - 1] = addc(a[NL - 1], b[NL - 1]);
+}
+// r = a - b, returns the borrow as an all-ones / all-zeros mask
+__device__ __forceinline__ uint32_t sub_raw(uint32_t *r, const uint32_t *a, const uint32_t *b) {
+    r[0] = sub_cc(a[0], b[0]);
+#pragma unroll
+    for (int i = 1; i < NL; ++i) r[i] = subc_cc(a[i], b[i]);
+    return subc(0u, 0u);  // 0 - 0 - borrow
+}
+// if a >= m: a -= m      (m = c_fp.p or c_fp.p2), branch free
+__device__ __forceinline__ void cond_sub(uint32_t *a, const uint32_t *m) {
+    uint32_t d[NL];
+    uint32_t borrow = sub_raw(d, a, m);
+#pragma unroll
+    for (int i = 0; i < NL; ++i) a[i] = borrow ? a[i] : d[i];
+}
+// lazy butterfly outputs: inputs u, t in [0, 2p)  ->  x = u + t, y = u - t, both in [0, 2p)
+__device__ __forceinline__ void add_lazy(uint32_t *x, const uint32_t *u, const uint32_t *t) {
+    add_raw(x, u, t);          // < 4p < 2^768
+    cond_sub(x, c_fp.p2);
+}
+__device__ __forceinline__ void sub_lazy(uint32_t *y, const uint32_t *u, const uint32_t *t) {
+    uint32_t borrow = sub_raw(y, u, t);   // in (-2p, 2p)
+    // y += borrow ? 2p : 0
+    y[0] = add_cc(y[0], c_fp.p2[0] & borrow);
+#pragma unroll
+    for (int i = 1; i < NL - 1; ++i) y[i] = addc_cc(y[i], c_fp.p2[i] & borrow);
+    y[NL - 1] = addc(y[NL - 1], c_fp.p2[NL - 1] & borrow);
+}
+// [0, 2p) -> [0, p)
+__device__ __forceinline__ void canonicalize(uint32_t *a) { cond_sub(a, c_fp.p); }
+
+// ------------------------------------------------------------------ Montgomery product
+// One outer CIOS step for multiplier word `bi` (reference: one pass of the `i` loop of
+// ciosMontgomeryMultiply, device_field_operators.h:156-184).  `ev`/`od` are the accumulators
+// aligned to even/odd limbs of the frame on entry to this step (see file header).
+template <bool FIRST>
+__device__ __forceinline__ void cios_step(uint32_t *ev, uint32_t *od, const uint32_t *a, uint32_t bi) {
+    if (FIRST) {
+#pragma unroll
+        for (int j = 0; j < NL; j += 2) mul_wide(od[j], od[j + 1], a[j + 1], bi);
+#pragma unroll
+        for (int j = 0; j < NL; j += 2) mul_wide(ev[j], ev[j + 1], a[j], bi);
+    } else {
+        // After the previous step's shift `od` (old even accumulator) still carries its
+        // limb 1 below this frame's first odd slot: fold it into ev[0], then accumulate
+        // the odd products while sliding `od` down by two limbs.
+        ev[0] = add_cc(ev[0], od[1]);
+#pragma unroll
+        for (int j = 0; j < NL - 2; j += 2) madc_wide_cc_from(od[j], od[j + 1], a[j + 1], bi, od[j + 2], od[j + 3]);
+        madc_wide_cc_from(od[NL - 2], od[NL - 1], a[NL - 1], bi, 0u, 0u);
+        mad_wide_cc(ev[0], ev[1], a[0], bi);
+#pragma unroll
+        for (int j = 2; j < NL; j += 2) madc_wide_cc(ev[j], ev[j + 1], a[j], bi);
+        od[NL - 1] = addc(od[NL - 1], 0u);
+    }
+    const uint32_t m = ev[0] * c_fp.np0;
+    mad_wide_cc(od[0], od[1], c_fp.p[1], m);
+#pragma unroll
+    for (int j = 2; j < NL; j += 2) madc_wide_cc(od[j], od[j + 1], c_fp.p[j + 1], m);
+    mad_wide_cc(ev[0], ev[1], c_fp.p[0], m);
+#pragma unroll
+    for (int j = 2; j < NL; j += 2) madc_wide_cc(ev[j], ev[j + 1], c_fp.p[j], m);
+    od[NL - 1] = addc(od[NL - 1], 0u);
+    // ev[0] is now 0 mod 2^32: the frame shifts right one limb, ev <-> od swap roles.
+}
+
+// r = a * b * 2^-768 mod p, result in [0, 2p) for a in [0, 2p), b < 2^768 (lazy: no final
+// subtraction).  `B` is any callable  uint32_t B(int i)  giving word i of b, so the
+// multiplier can stream from shared memory without occupying 24 registers.
+template <typename BWord>
+__device__ __forceinline__ void mont_mul_lazy_w(uint32_t *r, const uint32_t *a, BWord b) {
+    uint32_t ev[NL], od[NL];
+    cios_step<true>(ev, od, a, b(0));
+    cios_step<false>(od, ev, a, b(1));
+#pragma unroll
+    for (int i = 2; i < NL; i += 2) {
+        cios_step<false>(ev, od, a, b(i));
+        cios_step<false>(od, ev, a, b(i + 1));
+    }
+    // after an even number of steps `ev` is even-aligned again with ev[0] consumed:
+    // value = (ev >> 32) + od
+    r[0] = add_cc(ev[1], od[0]);
+#pragma unroll
+    for (int k = 1; k < NL - 1; ++k) r[k] = addc_cc(ev[k + 1], od[k]);
+    r[NL - 1] = addc(od[NL - 1], 0u);
+}
+
+struct RegWords {
+    const uint32_t *w;
+    __device__ __forceinline__ uint32_t operator()(int i) const { return w[i]; }
+};
+
+__device__ __forceinline__ void mont_mul_lazy(uint32_t *r, const uint32_t *a, const uint32_t *b) {
+    mont_mul_lazy_w(r, a, RegWords{b});
+}
+// canonical product, [0, p)
+__device__ __forceinline__ void mont_mul(uint32_t *r, const uint32_t *a, const uint32_t *b) {
+    mont_mul_lazy_w(r, a, RegWords{b});
+    canonicalize(r);
+}
+
+// ------------------------------------------------------------------ global memory access
+// elements are AoS, 96 bytes = 6 x 16 B, 32-byte aligned (reference layout: raw im_rep[24])
+__device__ __forceinline__ void load_elem(uint32_t *r, const uint32_t *g) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(g);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        uint4 v = p[c];
+        r[4 * c] = v.x; r[4 * c + 1] = v.y; r[4 * c + 2] = v.z; r[4 * c + 3] = v.w;
+    }
+}
+__device__ __forceinline__ void load_elem_nc(uint32_t *r, const uint32_t *g) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(g);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        uint4 v = __ldg(p + c);
+        r[4 * c] = v.x; r[4 * c + 1] = v.y; r[4 * c + 2] = v.z; r[4 * c + 3] = v.w;
+    }
+}
+__device__ __forceinline__ void store_elem(uint32_t *g, const uint32_t *r) {
+    uint4 *p = reinterpret_cast<uint4 *>(g);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) p[c] = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+}
+
+}  // namespace gsn

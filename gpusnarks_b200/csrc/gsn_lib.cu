@@ -1,0 +1,539 @@
+// gsn_lib.cu -- host planner + C ABI of libgpusnarks_b200.so (see include/gpusnarks_b200.h).
+//
+// Replaces the reference's host launcher best_fft (reference cuda/fft_kernel.cu:117-147):
+// where the reference cudaMallocs two buffers per call, copies, launches one kernel of
+// 5 x 256 threads and never frees, this keeps a context with a stream, a reusable
+// workspace and per-(n, omega) plans whose twiddle tables are computed on the device.
+// There is no CPU fallback: without a CUDA device every entry point fails with
+// GSN_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/gpusnarks_b200.h"
+#include "../../include/gsn_constants.h"
+#include "fp768.cuh"
+#include "host_fp768.h"
+#include "microbench.cuh"
+#include "ntt32.cuh"
+#include "ntt768.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) return fail(GSN_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr int MAX_PASS_LOG = 10;  // stages per shared-memory pass (tile of 1024 x 96 B)
+constexpr int NTT768_THREADS = 256;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+};
+
+struct Plan768 {
+    int field = 0;
+    uint32_t logn = 0;
+    int inverse = 0;
+    uint32_t omega[24];           // as passed by the caller (forward root)
+    std::vector<uint32_t> digits; // l_1..l_P
+    uint32_t lmax = 0;
+    DevBuf wloc;                  // w_T^k, k < T/2, T = 2^lmax
+    std::vector<std::unique_ptr<DevBuf>> pre;  // pre[q]: table read by pass q (nullptr if none)
+    std::vector<uint64_t> pre_mask;
+};
+
+struct Plan32 {
+    uint32_t mod = 0, omega = 0, logn = 0;
+    int inverse = 0;
+    std::vector<uint32_t> digits;
+    uint32_t lmax = 0;
+    DevBuf wloc;                  // pairs (w, w') Shoup form
+    std::vector<std::unique_ptr<DevBuf>> pre;
+    std::vector<uint64_t> pre_mask;
+};
+
+std::vector<uint32_t> plan_digits(uint32_t logn, uint32_t max_log) {
+    if (logn == 0) return {0};
+    const uint32_t npass = (logn + max_log - 1) / max_log;
+    const uint32_t base = logn / npass, extra = logn % npass;
+    std::vector<uint32_t> d(npass);
+    for (uint32_t i = 0; i < npass; ++i) d[i] = base + (i < extra ? 1 : 0);
+    return d;
+}
+
+bool is_pow2(size_t n) { return n && !(n & (n - 1)); }
+uint32_t ilog2(size_t n) { uint32_t l = 0; while (((size_t)1 << l) < n) ++l; return l; }
+
+}  // namespace
+
+struct gsn_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    int field = GSN_FIELD_MNT4753_FR;
+    gsn::FieldConstants768 fc;
+    gsn::host::Field768 hf;
+    int two_adicity = 30;
+    DevBuf work;
+    std::vector<std::unique_ptr<Plan768>> plans768;
+    std::vector<std::unique_ptr<Plan32>> plans32;
+    uint64_t launches = 0;
+    int sm_count = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool attr768_set = false, attr32_set = false;
+};
+
+namespace {
+
+int upload_field(gsn_ctx *ctx, int field) {
+    static const uint32_t fr_p[24] = GSN_FR_MOD, fr_p2[24] = GSN_FR_MOD2, fr_r1[24] = GSN_FR_R1, fr_r2[24] = GSN_FR_R2;
+    static const uint32_t fq_p[24] = GSN_FQ_MOD, fq_p2[24] = GSN_FQ_MOD2, fq_r1[24] = GSN_FQ_R1, fq_r2[24] = GSN_FQ_R2;
+    const bool fr = field == GSN_FIELD_MNT4753_FR;
+    memcpy(ctx->fc.p, fr ? fr_p : fq_p, 96);
+    memcpy(ctx->fc.p2, fr ? fr_p2 : fq_p2, 96);
+    memcpy(ctx->fc.r1, fr ? fr_r1 : fq_r1, 96);
+    memcpy(ctx->fc.r2, fr ? fr_r2 : fq_r2, 96);
+    ctx->fc.np0 = fr ? GSN_FR_NP0 : GSN_FQ_NP0;
+    ctx->two_adicity = fr ? GSN_FR_TWO_ADICITY : GSN_FQ_TWO_ADICITY;
+    ctx->hf.init(ctx->fc.p, ctx->fc.r1);
+    ctx->field = field;
+    CU(cudaMemcpyToSymbolAsync(gsn::c_fp, &ctx->fc, sizeof(ctx->fc), 0, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GSN_OK;
+}
+
+int ensure_work(gsn_ctx *ctx, size_t bytes) {
+    if (ctx->work.bytes >= bytes) return GSN_OK;
+    if (ctx->work.p) { cudaFree(ctx->work.p); ctx->work.p = nullptr; ctx->work.bytes = 0; }
+    cudaError_t e = cudaMalloc(&ctx->work.p, bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(GSN_ERR_TOO_LARGE, "workspace of %zu bytes: %s", bytes, cudaGetErrorString(e)); }
+    ctx->work.bytes = bytes;
+    return GSN_OK;
+}
+
+int dev_alloc(DevBuf &b, size_t bytes) {
+    cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); b.p = nullptr; return fail(GSN_ERR_TOO_LARGE, "table of %zu bytes: %s", bytes, cudaGetErrorString(e)); }
+    b.bytes = bytes;
+    return GSN_OK;
+}
+
+// ------------------------------------------------------------------------------ 768-bit plans
+int validate_omega768(gsn_ctx *ctx, const uint32_t *omega, uint32_t logn) {
+    uint64_t w[12];
+    memcpy(w, omega, 96);
+    if (!gsn::host::Field768::geq(ctx->hf.p, w) || memcmp(w, ctx->hf.p, 96) == 0)
+        return fail(GSN_ERR_BAD_OMEGA, "omega is not reduced modulo p");
+    if (logn == 0) return ctx->hf.is_one(w) ? GSN_OK : fail(GSN_ERR_BAD_OMEGA, "n = 1 needs omega = one()");
+    for (uint32_t i = 0; i + 1 < logn; ++i) ctx->hf.mul(w, w, w);  // w^(n/2)
+    if (!ctx->hf.is_minus_one(w)) return fail(GSN_ERR_BAD_OMEGA, "omega^(n/2) != -1: not a primitive 2^%u-th root of unity", logn);
+    return GSN_OK;
+}
+
+int get_plan768(gsn_ctx *ctx, uint32_t logn, const uint32_t *omega, int inverse, Plan768 **out) {
+    for (auto &pl : ctx->plans768)
+        if (pl->field == ctx->field && pl->logn == logn && pl->inverse == (inverse != 0) && memcmp(pl->omega, omega, 96) == 0) {
+            *out = pl.get();
+            return GSN_OK;
+        }
+    if ((int)logn > ctx->two_adicity) return fail(GSN_ERR_TOO_LARGE, "n = 2^%u exceeds the field's 2-adicity %d", logn, ctx->two_adicity);
+    int rc = validate_omega768(ctx, omega, logn);
+    if (rc) return rc;
+
+    auto pl = std::make_unique<Plan768>();
+    pl->field = ctx->field;
+    pl->logn = logn;
+    pl->inverse = inverse != 0;
+    memcpy(pl->omega, omega, 96);
+    pl->digits = plan_digits(logn, MAX_PASS_LOG);
+    pl->lmax = *std::max_element(pl->digits.begin(), pl->digits.end());
+    const size_t P = pl->digits.size();
+    pl->pre.resize(P);
+    pl->pre_mask.assign(P, 0);
+
+    const uint64_t n = 1ull << logn;
+    // effective root (omega or omega^-1 = omega^(n-1)) and n^-1, Montgomery form, on the host
+    uint64_t w_eff[12], n_inv[12];
+    memcpy(w_eff, omega, 96);
+    if (inverse) {
+        ctx->hf.pow(w_eff, w_eff, n - 1);
+        memcpy(n_inv, ctx->hf.r1, 96);
+        for (uint32_t i = 0; i < logn; ++i) ctx->hf.halve(n_inv, n_inv);
+    }
+    cudaStream_t st = ctx->stream;
+    DevBuf d_w, d_ninv, t_lo, t_hi;
+    if ((rc = dev_alloc(d_w, 96))) return rc;
+    CU(cudaMemcpyAsync(d_w.p, w_eff, 96, cudaMemcpyHostToDevice, st));
+    if (inverse) {
+        if ((rc = dev_alloc(d_ninv, 96))) return rc;
+        CU(cudaMemcpyAsync(d_ninv.p, n_inv, 96, cudaMemcpyHostToDevice, st));
+    }
+    // local table: w_T^k, k < T/2
+    const uint64_t half = pl->lmax ? (1ull << (pl->lmax - 1)) : 1;
+    if ((rc = dev_alloc(pl->wloc, half * 96))) return rc;
+    gsn::pow_table768<<<(unsigned)((half + 127) / 128), 128, 0, st>>>((uint32_t *)pl->wloc.p, (const uint32_t *)d_w.p, half,
+                                                                        pl->lmax ? (n >> pl->lmax) : 0);
+    ctx->launches++;
+    if (P > 1) {
+        const uint32_t lo_bits = std::min<uint32_t>(10, logn);
+        if ((rc = dev_alloc(t_lo, (1ull << lo_bits) * 96))) return rc;
+        if ((rc = dev_alloc(t_hi, (n >> lo_bits) * 96))) return rc;
+        gsn::pow_table768<<<(unsigned)(((1ull << lo_bits) + 127) / 128), 128, 0, st>>>((uint32_t *)t_lo.p, (const uint32_t *)d_w.p, 1ull << lo_bits, 1);
+        gsn::pow_table768<<<(unsigned)(((n >> lo_bits) + 127) / 128), 128, 0, st>>>((uint32_t *)t_hi.p, (const uint32_t *)d_w.p, n >> lo_bits, 1ull << lo_bits);
+        ctx->launches += 2;
+        // boundaries are built last-to-first so that, for an inverse plan, the low table can be
+        // scaled by n^-1 in place just before boundary 1 (which thereby carries the scaling)
+        for (size_t q = P - 1; q >= 1; --q) {
+            uint32_t logN = 0;
+            for (size_t i = q - 1; i < P; ++i) logN += pl->digits[i];
+            const uint32_t rest_bits = logN - pl->digits[q - 1];
+            if (q == 1 && inverse) {
+                const uint64_t cnt = 1ull << lo_bits;
+                gsn::scale_table768<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>((uint32_t *)t_lo.p, (const uint32_t *)t_lo.p, (const uint32_t *)d_ninv.p, cnt);
+                ctx->launches++;
+            }
+            pl->pre[q] = std::make_unique<DevBuf>();
+            if ((rc = dev_alloc(*pl->pre[q], (1ull << logN) * 96))) return rc;
+            pl->pre_mask[q] = (1ull << logN) - 1;
+            const uint64_t cnt = 1ull << logN;
+            gsn::build_pretw768<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>((uint32_t *)pl->pre[q]->p, (const uint32_t *)t_lo.p, (const uint32_t *)t_hi.p,
+                                                                                logN, rest_bits, logn - logN, lo_bits);
+            ctx->launches++;
+        }
+    } else if (inverse) {
+        pl->pre[0] = std::make_unique<DevBuf>();
+        if ((rc = dev_alloc(*pl->pre[0], 96))) return rc;
+        CU(cudaMemcpyAsync(pl->pre[0]->p, n_inv, 96, cudaMemcpyHostToDevice, st));
+        pl->pre_mask[0] = 0;
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    *out = pl.get();
+    ctx->plans768.push_back(std::move(pl));
+    return GSN_OK;
+}
+
+int launch_ntt768(gsn_ctx *ctx, Plan768 *pl, uint32_t *d_data, size_t batch, uint32_t log_r, cudaStream_t st) {
+    const size_t P = pl->digits.size();
+    const uint64_t total = (uint64_t)batch << (pl->logn + log_r);
+    uint32_t v2 = 0;
+    while (v2 < 10 && !((total >> v2) & 1)) ++v2;
+    const uint32_t log_tile = v2;  // min(10, 2-adic valuation of total) >= every digit
+    int rc;
+    if (P > 1 && (rc = ensure_work(ctx, total * 96))) return rc;
+    uint32_t *work = (uint32_t *)ctx->work.p;
+
+    auto kern = gsn::ntt768_pass<NTT768_THREADS, 2>;
+    if (!ctx->attr768_set) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << MAX_PASS_LOG) * gsn::SMEM_PITCH4 * 16));
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        ctx->attr768_set = true;
+    }
+    uint32_t below = log_r;
+    for (size_t i = 0; i < P; ++i) below += pl->digits[i];
+    for (size_t q = 0; q < P; ++q) {
+        below -= pl->digits[q];
+        gsn::PassGeom g;
+        memset(&g, 0, sizeof(g));
+        g.log_l = pl->digits[q];
+        g.log_s = below;
+        g.log_r = log_r;
+        g.log_tile = log_tile;
+        g.wloc_shift = pl->lmax - pl->digits[q];
+        g.final_natural = q + 1 == P;
+        g.canonical = q + 1 == P;
+        g.ndig = (uint32_t)P;
+        for (size_t i = 0; i < P; ++i) g.dig[i] = pl->digits[i];
+        g.logn = pl->logn;
+        g.has_pre = pl->pre[q] != nullptr;
+        g.pre_mask = pl->pre_mask[q];
+        // pass 1 reads the caller's buffer, the last pass writes it; middle passes run in
+        // place in the workspace (a tile reads and writes the same index set).
+        const uint32_t *src = q == 0 ? d_data : work;
+        uint32_t *dst = (q + 1 == P) ? d_data : work;
+        const size_t smem = ((size_t)1 << log_tile) * gsn::SMEM_PITCH4 * 16;
+        kern<<<(unsigned)(total >> log_tile), NTT768_THREADS, smem, st>>>(src, dst, (const uint32_t *)pl->wloc.p,
+                                                                           g.has_pre ? (const uint32_t *)pl->pre[q]->p : nullptr, g);
+        ctx->launches++;
+    }
+    CU(cudaGetLastError());
+    return GSN_OK;
+}
+
+int check_n(size_t n, size_t batch) {
+    if (!is_pow2(n)) return fail(GSN_ERR_NOT_POW2, "n = %zu is not a power of two", n);
+    if (batch == 0) return fail(GSN_ERR_INVALID_ARG, "batch = 0");
+    return GSN_OK;
+}
+
+}  // namespace
+
+#include "ntt32_host.inl"
+
+extern "C" {
+
+const char *gsn_last_error(void) { return g_err.c_str(); }
+
+int gsn_device_count(int *count) {
+    if (!count) return fail(GSN_ERR_INVALID_ARG, "null count");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) { *count = 0; cudaGetLastError(); return fail(GSN_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    return GSN_OK;
+}
+
+int gsn_ctx_create(gsn_ctx **out, int device) {
+    if (!out) return fail(GSN_ERR_INVALID_ARG, "null ctx pointer");
+    *out = nullptr;
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt == 0) {
+        cudaGetLastError();
+        return fail(GSN_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU fallback", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= cnt) return fail(GSN_ERR_INVALID_ARG, "device %d out of range (%d devices)", device, cnt);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(GSN_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    std::unique_ptr<gsn_ctx> ctx(new gsn_ctx());
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&ctx->ev0));
+    CU(cudaEventCreate(&ctx->ev1));
+    int rc = upload_field(ctx.get(), GSN_FIELD_MNT4753_FR);
+    if (rc) return rc;
+    *out = ctx.release();
+    return GSN_OK;
+}
+
+int gsn_ctx_destroy(gsn_ctx *ctx) {
+    if (!ctx) return GSN_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->plans768.clear();
+    ctx->plans32.clear();
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return GSN_OK;
+}
+
+int gsn_ctx_trim(gsn_ctx *ctx) {
+    if (!ctx) return fail(GSN_ERR_INVALID_ARG, "null ctx");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->plans768.clear();
+    ctx->plans32.clear();
+    if (ctx->work.p) { cudaFree(ctx->work.p); ctx->work.p = nullptr; ctx->work.bytes = 0; }
+    return GSN_OK;
+}
+
+int gsn_launch_count(gsn_ctx *ctx, uint64_t *count) {
+    if (!ctx || !count) return fail(GSN_ERR_INVALID_ARG, "null argument");
+    *count = ctx->launches;
+    return GSN_OK;
+}
+
+int gsn_set_field768(gsn_ctx *ctx, int field) {
+    if (!ctx) return fail(GSN_ERR_INVALID_ARG, "null ctx");
+    if (field != GSN_FIELD_MNT4753_FR && field != GSN_FIELD_MNT4753_FQ) return fail(GSN_ERR_INVALID_ARG, "unknown field %d", field);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    return upload_field(ctx, field);
+}
+
+int gsn_ntt768_prepare(gsn_ctx *ctx, size_t n, size_t batch, const uint32_t *omega, int inverse) {
+    if (!ctx || !omega) return fail(GSN_ERR_INVALID_ARG, "null argument");
+    int rc = check_n(n, batch);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    Plan768 *pl;
+    if ((rc = get_plan768(ctx, ilog2(n), omega, inverse, &pl))) return rc;
+    if (pl->digits.size() > 1) return ensure_work(ctx, (size_t)batch * n * 96);
+    return GSN_OK;
+}
+
+int gsn_ntt768_strided_device(gsn_ctx *ctx, uint32_t *d_limbs, size_t n, size_t batch, unsigned log_r, const uint32_t *omega,
+                              int inverse, void *stream) {
+    if (!ctx || !d_limbs || !omega) return fail(GSN_ERR_INVALID_ARG, "null argument");
+    int rc = check_n(n, batch);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    Plan768 *pl;
+    if ((rc = get_plan768(ctx, ilog2(n), omega, inverse, &pl))) return rc;
+    return launch_ntt768(ctx, pl, d_limbs, batch, log_r, stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+int gsn_ntt768_device(gsn_ctx *ctx, uint32_t *d_limbs, size_t n, size_t batch, const uint32_t *omega, int inverse, void *stream) {
+    return gsn_ntt768_strided_device(ctx, d_limbs, n, batch, 0, omega, inverse, stream);
+}
+
+int gsn_ntt768_host(gsn_ctx *ctx, uint32_t *limbs, size_t n, const uint32_t *omega, int inverse) {
+    if (!ctx || !limbs || !omega) return fail(GSN_ERR_INVALID_ARG, "null argument");
+    int rc = check_n(n, 1);
+    if (rc) return rc;
+    DevBuf d;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        CU(cudaSetDevice(ctx->device));
+        if ((rc = dev_alloc(d, n * 96))) return rc;
+        CU(cudaMemcpyAsync(d.p, limbs, n * 96, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if ((rc = gsn_ntt768_device(ctx, (uint32_t *)d.p, n, 1, omega, inverse, nullptr))) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaMemcpyAsync(limbs, d.p, n * 96, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GSN_OK;
+}
+
+int gsn_ntt768_time_device(gsn_ctx *ctx, uint32_t *d_limbs, size_t n, size_t batch, const uint32_t *omega, int inverse, int reps,
+                           float *ms_each) {
+    if (!ctx || !d_limbs || !omega || !ms_each || reps <= 0) return fail(GSN_ERR_INVALID_ARG, "bad argument");
+    int rc = gsn_ntt768_prepare(ctx, n, batch, omega, inverse);
+    if (rc) return rc;
+    for (int i = 0; i < reps; ++i) {
+        CU(cudaEventRecord(ctx->ev0, ctx->stream));
+        if ((rc = gsn_ntt768_device(ctx, d_limbs, n, batch, omega, inverse, nullptr))) return rc;
+        CU(cudaEventRecord(ctx->ev1, ctx->stream));
+        CU(cudaEventSynchronize(ctx->ev1));
+        CU(cudaEventElapsedTime(&ms_each[i], ctx->ev0, ctx->ev1));
+    }
+    return GSN_OK;
+}
+
+int gsn_fp768_binop_host(gsn_ctx *ctx, int op, uint32_t *out, const uint32_t *a, const uint32_t *b, size_t count) {
+    if (!ctx || !out || !a || !b) return fail(GSN_ERR_INVALID_ARG, "null argument");
+    if (op < 0 || op > 2) return fail(GSN_ERR_INVALID_ARG, "op %d", op);
+    if (count == 0) return GSN_OK;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    DevBuf da, db, dc;
+    int rc;
+    if ((rc = dev_alloc(da, count * 96)) || (rc = dev_alloc(db, count * 96)) || (rc = dev_alloc(dc, count * 96))) return rc;
+    CU(cudaMemcpyAsync(da.p, a, count * 96, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(db.p, b, count * 96, cudaMemcpyHostToDevice, ctx->stream));
+    gsn::binop768<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>((uint32_t *)dc.p, (const uint32_t *)da.p, (const uint32_t *)db.p, count, op);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, dc.p, count * 96, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GSN_OK;
+}
+
+int gsn_fp768_twiddle_device(gsn_ctx *ctx, uint32_t *d_limbs, size_t rows, size_t cols, size_t row0, size_t col0, size_t n_total,
+                             const uint32_t *omega, void *stream) {
+    (void)ctx; (void)d_limbs; (void)rows; (void)cols; (void)row0; (void)col0; (void)n_total; (void)omega; (void)stream;
+    return fail(GSN_ERR_INVALID_ARG, "gsn_fp768_twiddle_device: not built yet");
+}
+
+// ---- helpers
+int gsn_host_alloc(void **ptr, size_t bytes) {
+    if (!ptr) return fail(GSN_ERR_INVALID_ARG, "null ptr");
+    CU(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    return GSN_OK;
+}
+int gsn_host_free(void *ptr) { CU(cudaFreeHost(ptr)); return GSN_OK; }
+int gsn_device_alloc(gsn_ctx *ctx, void **dptr, size_t bytes) {
+    if (!ctx || !dptr) return fail(GSN_ERR_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(dptr, bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(GSN_ERR_TOO_LARGE, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
+    return GSN_OK;
+}
+int gsn_device_free(gsn_ctx *ctx, void *dptr) {
+    if (!ctx) return fail(GSN_ERR_INVALID_ARG, "null ctx");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaFree(dptr));
+    return GSN_OK;
+}
+int gsn_memcpy_h2d(gsn_ctx *ctx, void *dptr, const void *hptr, size_t bytes) {
+    if (!ctx) return fail(GSN_ERR_INVALID_ARG, "null ctx");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(dptr, hptr, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GSN_OK;
+}
+int gsn_memcpy_d2h(gsn_ctx *ctx, void *hptr, const void *dptr, size_t bytes) {
+    if (!ctx) return fail(GSN_ERR_INVALID_ARG, "null ctx");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(hptr, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GSN_OK;
+}
+int gsn_ctx_synchronize(gsn_ctx *ctx) {
+    if (!ctx) return fail(GSN_ERR_INVALID_ARG, "null ctx");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GSN_OK;
+}
+
+// ---- INT32 issue-rate probe
+int gsn_int32_issue_rates(gsn_ctx *ctx, double rates[5], int *sm_count, int *sm_clock_khz) {
+    if (!ctx || !rates) return fail(GSN_ERR_INVALID_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    DevBuf sink;
+    int rc;
+    if ((rc = dev_alloc(sink, 256))) return rc;
+    const int iters = 8192, blocks = ctx->sm_count * 8, threads = 256;
+    for (int mode = 0; mode < 5; ++mode) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            CU(cudaEventRecord(ctx->ev0, ctx->stream));
+            switch (mode) {
+                case 0: gsn::int32_issue_probe<0><<<blocks, threads, 0, ctx->stream>>>((uint32_t *)sink.p, 12345u + rep, iters); break;
+                case 1: gsn::int32_issue_probe<1><<<blocks, threads, 0, ctx->stream>>>((uint32_t *)sink.p, 12345u + rep, iters); break;
+                case 2: gsn::int32_issue_probe<2><<<blocks, threads, 0, ctx->stream>>>((uint32_t *)sink.p, 12345u + rep, iters); break;
+                case 3: gsn::int32_issue_probe<3><<<blocks, threads, 0, ctx->stream>>>((uint32_t *)sink.p, 12345u + rep, iters); break;
+                default: gsn::int32_issue_probe<4><<<blocks, threads, 0, ctx->stream>>>((uint32_t *)sink.p, 12345u + rep, iters); break;
+            }
+            ctx->launches++;
+            CU(cudaEventRecord(ctx->ev1, ctx->stream));
+            CU(cudaEventSynchronize(ctx->ev1));
+            float ms;
+            CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+            if (rep > 0) best = std::min(best, ms);
+        }
+        const double ops = (double)blocks * threads * iters * gsn::int32_probe_ops_per_iter(mode);
+        rates[mode] = ops / (best * 1e-3);
+    }
+    CU(cudaGetLastError());
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (sm_clock_khz) { int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device); *sm_clock_khz = khz; }
+    return GSN_OK;
+}
+
+}  // extern "C"

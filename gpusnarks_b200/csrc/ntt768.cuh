@@ -1,0 +1,248 @@
+// ntt768.cuh -- multi-pass radix-2 NTT over the 768-bit field, sm_100a.
+//
+// Replaces reference cuda/fft_kernel.cu:52-115 (`cuda_fft`, an O(n * 1024) routine hard
+// wired to n = 2^16 that ignores omega) with an O(n log n) transform for any power of two.
+// The index math is the one modelled and checked in tools/model_passes.py (`run_pass`).
+//
+// Decomposition.  log2(n) is split into P "digits" l_1..l_P (each <= 10); the input index is
+// read as mixed radix (d_1 .. d_P | r) with d_1 most significant and an optional inner
+// stride 2^log_r, pass q transforms digit d_q into k_q, and the last pass writes the digits
+// in reversed significance (k_P .. k_1 | r): natural order in, natural order out.  Between
+// passes every element is multiplied by w_{N_q}^(k_{q-1} * (d_q..d_P)) from a device table
+// (four-step / Bailey twiddles, built once per (n, omega) by build_pretw768).
+//
+// One CTA owns one tile of 2^log_tile (<= 1024) elements = 2^(log_tile - l_q) sub-transforms:
+//   load   global -> shared, bit-reversed placement (the reference's swap loop,
+//          test/fft_host.h:24-29, fused into the load)
+//   mul    optional pre-twiddle, one Montgomery product per element
+//   stages l_q radix-2 DIT butterfly stages in shared memory (test/fft_host.h:31-53 with the
+//          twiddle read from a table instead of the running product w *= w_m)
+//   store  shared -> global (in-place position, or digit-reversed for the last pass)
+// All Montgomery products of the kernel go through ONE inlined call site (the `ph` loop):
+// the product is ~1.2k instructions, and a single copy keeps the kernel inside the
+// instruction cache.  Stage 1 has unit twiddles and skips the product.
+//
+// Shared memory layout: AoS with a 112-byte pitch (96 B of limbs + 16 B pad).  With a
+// 28-word pitch the eight lanes of a quarter-warp that read the same 16-byte chunk of eight
+// consecutive elements hit eight distinct bank groups, so LDS.128/STS.128 are conflict
+// free for every stage with half-distance >= 8.
+#pragma once
+#include "fp768.cuh"
+
+namespace gsn {
+
+constexpr int SMEM_PITCH4 = 7;  // uint4 per element in shared memory (112 B)
+
+struct PassGeom {
+    uint32_t log_l;          // stages of this pass (digit width)
+    uint32_t log_s;          // log2 stride (elements) of this digit
+    uint32_t log_r;          // log2 inner stride (pre-twiddle index = (g >> log_r) & pre_mask)
+    uint32_t log_tile;       // log2 elements per CTA tile (>= log_l)
+    uint32_t wloc_shift;     // local table index = (jj << (log_l - s)) << wloc_shift
+    uint32_t final_natural;  // last pass: write digits reversed
+    uint32_t canonical;      // outputs reduced to [0, p) (else lazy [0, 2p))
+    uint32_t ndig;           // number of digits of the whole transform
+    uint32_t dig[4];         // digit widths l_1..l_P
+    uint32_t logn;           // sum of digits
+    uint32_t has_pre;        // pre-twiddle table present
+    uint64_t pre_mask;       // 0 => scalar pre-multiply (pre_tw[0])
+};
+
+__device__ __forceinline__ uint64_t elem_index(const PassGeom &g, uint64_t t, uint32_t j) {
+    const uint64_t o = t >> g.log_s, rlow = t & ((1ull << g.log_s) - 1);
+    return (((o << g.log_l) | j) << g.log_s) | rlow;
+}
+
+__device__ __forceinline__ uint64_t out_index(const PassGeom &g, uint64_t t, uint32_t k) {
+    if (!g.final_natural) return elem_index(g, t, k);
+    // t = (o | r) with o = (batch, k_1 .. k_{P-1}), log_s == log_r
+    const uint64_t o = t >> g.log_s, rlow = t & ((1ull << g.log_s) - 1);
+    const uint32_t inner_bits = g.logn - g.log_l;
+    const uint64_t batch = o >> inner_bits;
+    const uint64_t rest = o & ((1ull << inner_bits) - 1);
+    uint64_t out = 0;
+    uint32_t shift = 0, pos = inner_bits;
+    for (uint32_t q = 0; q + 1 < g.ndig; ++q) {
+        pos -= g.dig[q];
+        out |= ((rest >> pos) & ((1ull << g.dig[q]) - 1)) << shift;
+        shift += g.dig[q];
+    }
+    out |= (uint64_t)k << shift;
+    return (((batch << g.logn) | out) << g.log_r) | rlow;
+}
+
+// multiplier words streamed from shared memory, one LDS.128 per four limbs
+struct SmemWords {
+    const uint4 *p;
+    uint4 cur;
+    __device__ __forceinline__ uint32_t operator()(int i) {
+        if ((i & 3) == 0) cur = p[i >> 2];
+        return (i & 3) == 0 ? cur.x : (i & 3) == 1 ? cur.y : (i & 3) == 2 ? cur.z : cur.w;
+    }
+};
+
+__device__ __forceinline__ void lds_elem(uint32_t *r, const uint4 *s) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        uint4 v = s[c];
+        r[4 * c] = v.x; r[4 * c + 1] = v.y; r[4 * c + 2] = v.z; r[4 * c + 3] = v.w;
+    }
+}
+__device__ __forceinline__ void sts_elem(uint4 *s, const uint32_t *r) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) s[c] = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+}
+
+template <int THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
+ntt768_pass(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, const uint32_t *__restrict__ wloc,
+            const uint32_t *__restrict__ pre_tw, const PassGeom g) {
+    extern __shared__ uint4 tile[];
+    const uint32_t T = 1u << g.log_tile;
+    const uint32_t lq = g.log_l;
+    const uint32_t Lm1 = (1u << lq) - 1;
+    const uint64_t sub0 = (uint64_t)blockIdx.x << (g.log_tile - lq);  // first sub-transform of this tile
+
+    // ---- load: thread per element, 6 x LDG.128, bit-reversed placement inside its sub-transform
+    for (uint32_t e = threadIdx.x; e < T; e += THREADS) {
+        const uint32_t slot = e >> lq, j = e & Lm1;
+        const uint64_t gi = elem_index(g, sub0 + slot, j);
+        const uint4 *p = reinterpret_cast<const uint4 *>(src + gi * NL);
+        const uint32_t pos = (slot << lq) | (lq ? (__brev(j) >> (32 - lq)) : 0u);
+        uint4 *s = tile + pos * SMEM_PITCH4;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) s[c] = p[c];
+    }
+    __syncthreads();
+
+    // ---- ph = 0: pre-twiddle (one product per element); ph = s >= 1: butterfly stage s
+    for (uint32_t ph = g.has_pre ? 0u : 1u; ph <= lq; ++ph) {
+        const uint32_t work = ph == 0 ? T : (T >> 1);
+        for (uint32_t b = threadIdx.x; b < work; b += THREADS) {
+            uint32_t lo = 0, hi;
+            const uint32_t *wp;
+            if (ph == 0) {
+                hi = b;
+                const uint32_t slot = b >> lq;
+                const uint32_t j = lq ? (__brev(b & Lm1) >> (32 - lq)) : 0u;
+                const uint64_t gi = elem_index(g, sub0 + slot, j);
+                wp = pre_tw + ((gi >> g.log_r) & g.pre_mask) * NL;
+            } else {
+                const uint32_t m = 1u << (ph - 1);
+                const uint32_t jj = b & (m - 1);
+                lo = ((b >> (ph - 1)) << ph) | jj;
+                hi = lo + m;
+                wp = wloc + (size_t)((jj << (lq - ph)) << g.wloc_shift) * NL;
+            }
+            uint4 *sh = tile + hi * SMEM_PITCH4;
+            uint32_t t[NL];
+            if (ph == 1) {
+                lds_elem(t, sh);  // unit twiddle
+            } else {
+                uint32_t w[NL];
+                load_elem_nc(w, wp);
+                SmemWords bw{sh, make_uint4(0, 0, 0, 0)};
+                mont_mul_lazy_w(t, w, bw);
+            }
+            if (ph == 0) {
+                sts_elem(sh, t);
+            } else {
+                uint4 *sl = tile + lo * SMEM_PITCH4;
+                uint32_t u[NL], x[NL];
+                lds_elem(u, sl);
+                add_lazy(x, u, t);
+                if (g.canonical && ph == lq) canonicalize(x);
+                sts_elem(sl, x);
+                sub_lazy(x, u, t);
+                if (g.canonical && ph == lq) canonicalize(x);
+                sts_elem(sh, x);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- store
+    for (uint32_t e = threadIdx.x; e < T; e += THREADS) {
+        const uint32_t slot = e >> lq, k = e & Lm1;
+        const uint64_t go = out_index(g, sub0 + slot, k);
+        uint4 *p = reinterpret_cast<uint4 *>(dst + go * NL);
+        const uint4 *s = tile + e * SMEM_PITCH4;
+        if (lq == 0 && g.canonical) {  // degenerate n = 1 transforms still leave canonical values
+            uint32_t x[NL];
+            lds_elem(x, s);
+            canonicalize(x);
+            store_elem(dst + go * NL, x);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) p[c] = s[c];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ table builders
+// out[k] = base^(k * stride), k < count   (square and multiply per thread; tables are tiny
+// compared with the transform and are cached per (n, omega))
+__global__ void pow_table768(uint32_t *out, const uint32_t *base, uint64_t count, uint64_t stride) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    uint32_t b[NL], acc[NL];
+    load_elem(b, base);
+#pragma unroll
+    for (int i = 0; i < NL; ++i) acc[i] = c_fp.r1[i];
+    const uint64_t e = k * stride;
+    const int top = 63 - __clzll((long long)(e | 1));
+    for (int bit = top; bit >= 0; --bit) {
+        uint32_t t[NL];
+        mont_mul_lazy(t, acc, acc);
+        if ((e >> bit) & 1) mont_mul_lazy(acc, t, b);
+        else {
+#pragma unroll
+            for (int i = 0; i < NL; ++i) acc[i] = t[i];
+        }
+    }
+    canonicalize(acc);
+    store_elem(out + k * NL, acc);
+}
+
+// Pre-twiddle table of one pass boundary: out[idx] = w_n^(((k * rest) mod N) << exp_shift),
+// idx = (k << rest_bits) | rest, assembled from the two-level tables
+//   t_lo[e] = w_n^e (e < 2^lo_bits),  t_hi[e] = w_n^(e << lo_bits).
+__global__ void build_pretw768(uint32_t *out, const uint32_t *t_lo, const uint32_t *t_hi, uint32_t logN,
+                               uint32_t rest_bits, uint32_t exp_shift, uint32_t lo_bits) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >> logN) return;
+    const uint64_t k = idx >> rest_bits, rest = idx & ((1ull << rest_bits) - 1);
+    const uint64_t e = ((k * rest) & ((1ull << logN) - 1)) << exp_shift;
+    uint32_t a[NL], b[NL], r[NL];
+    load_elem(a, t_lo + (e & ((1ull << lo_bits) - 1)) * NL);
+    load_elem(b, t_hi + (e >> lo_bits) * NL);
+    mont_mul(r, a, b);
+    store_elem(out + idx * NL, r);
+}
+
+// out[i] = a[i] * s   (canonical); used to fold n^-1 into a table
+__global__ void scale_table768(uint32_t *out, const uint32_t *a, const uint32_t *s, uint64_t count) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint32_t x[NL], y[NL], r[NL];
+    load_elem(x, a + i * NL);
+    load_elem(y, s);
+    mont_mul(r, x, y);
+    store_elem(out + i * NL, r);
+}
+
+// element-wise field ops for the arithmetic parity tests (canonical results)
+// op: 0 mul, 1 add, 2 sub
+__global__ void binop768(uint32_t *out, const uint32_t *a, const uint32_t *b, uint64_t count, int op) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint32_t x[NL], y[NL], r[NL];
+    load_elem(x, a + i * NL);
+    load_elem(y, b + i * NL);
+    if (op == 0) mont_mul(r, x, y);
+    else if (op == 1) { add_lazy(r, x, y); canonicalize(r); }
+    else { sub_lazy(r, x, y); canonicalize(r); }
+    store_elem(out + i * NL, r);
+}
+
+}  // namespace gsn

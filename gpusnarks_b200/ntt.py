@@ -1,0 +1,162 @@
+"""Host-side Python face of the C ABI (include/gpusnarks_b200.h).
+
+Mirrors the reference's operator interface for the FFT path: `best_fft(a, omega)` transforms
+a vector of field elements in place given a root of unity (reference cuda/fft_kernel.h:24-25,
+test/main.cpp:57).  Elements are numpy uint32 arrays: shape (n, 24) for the 768-bit field
+(`fields::Scalar::im_rep`, little-endian limbs, Montgomery form) and shape (n,) for the 32-bit
+field (`dummy_fields::Field::im_rep`).  All compute happens in the CUDA library.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+FIELD_FR = 0
+FIELD_FQ = 1
+NL = 24
+
+ERRORS = {1: "INVALID_ARG", 2: "NOT_POW2", 3: "TOO_LARGE", 4: "BAD_OMEGA", 5: "CUDA", 6: "NO_DEVICE", 7: "BAD_MODULUS"}
+
+
+class GsnError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"GSN_ERR_{ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _limbs(a, shape_tail=(NL,)):
+    a = np.ascontiguousarray(a, dtype=np.uint32)
+    return a
+
+
+class Context:
+    """gsn_ctx: one stream, one workspace, cached twiddle plans."""
+
+    def __init__(self, device=0):
+        self.L = _lib.load()
+        h = C.c_void_p()
+        self._h = None
+        self._check(self.L.gsn_ctx_create(C.byref(h), int(device)))
+        self._h = h
+        self.device = device
+
+    def _check(self, rc):
+        if rc != 0:
+            raise GsnError(rc, self.L.gsn_last_error().decode())
+
+    def close(self):
+        if self._h is not None:
+            self.L.gsn_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- configuration
+    def set_field768(self, field):
+        self._check(self.L.gsn_set_field768(self._h, int(field)))
+
+    def trim(self):
+        self._check(self.L.gsn_ctx_trim(self._h))
+
+    def launch_count(self):
+        c = C.c_uint64()
+        self._check(self.L.gsn_launch_count(self._h, C.byref(c)))
+        return c.value
+
+    def synchronize(self):
+        self._check(self.L.gsn_ctx_synchronize(self._h))
+
+    # ---- memory helpers
+    def device_alloc(self, nbytes):
+        p = C.c_void_p()
+        self._check(self.L.gsn_device_alloc(self._h, C.byref(p), int(nbytes)))
+        return p.value
+
+    def device_free(self, dptr):
+        self._check(self.L.gsn_device_free(self._h, C.c_void_p(dptr)))
+
+    def h2d(self, dptr, arr):
+        arr = np.ascontiguousarray(arr)
+        self._check(self.L.gsn_memcpy_h2d(self._h, C.c_void_p(dptr), _ptr(arr), arr.nbytes))
+
+    def d2h(self, arr, dptr):
+        assert arr.flags["C_CONTIGUOUS"]
+        self._check(self.L.gsn_memcpy_d2h(self._h, _ptr(arr), C.c_void_p(dptr), arr.nbytes))
+
+    # ---- 768-bit field
+    def best_fft768(self, a, omega, inverse=False):
+        """in-place transform of a host (n, 24) uint32 array -- the reference's best_fft<Scalar>"""
+        assert a.dtype == np.uint32 and a.flags["C_CONTIGUOUS"] and a.ndim == 2 and a.shape[1] == NL
+        omega = _limbs(omega)
+        self._check(self.L.gsn_ntt768_host(self._h, _ptr(a), a.shape[0], _ptr(omega), int(bool(inverse))))
+        return a
+
+    def ntt768(self, a, omega, inverse=False):
+        out = np.ascontiguousarray(a, dtype=np.uint32).reshape(-1, NL).copy()
+        return self.best_fft768(out, omega, inverse)
+
+    def ntt768_device(self, dptr, n, omega, inverse=False, batch=1, log_r=0, stream=None):
+        omega = _limbs(omega)
+        self._check(self.L.gsn_ntt768_strided_device(self._h, C.c_void_p(dptr), int(n), int(batch), int(log_r), _ptr(omega),
+                                                     int(bool(inverse)), C.c_void_p(stream or 0)))
+
+    def prepare768(self, n, omega, inverse=False, batch=1):
+        omega = _limbs(omega)
+        self._check(self.L.gsn_ntt768_prepare(self._h, int(n), int(batch), _ptr(omega), int(bool(inverse))))
+
+    def time_ntt768(self, dptr, n, omega, inverse=False, batch=1, reps=10):
+        omega = _limbs(omega)
+        ms = (C.c_float * reps)()
+        self._check(self.L.gsn_ntt768_time_device(self._h, C.c_void_p(dptr), int(n), int(batch), _ptr(omega), int(bool(inverse)), reps, ms))
+        return list(ms)
+
+    def fp768_binop(self, op, a, b):
+        a = np.ascontiguousarray(a, dtype=np.uint32).reshape(-1, NL)
+        b = np.ascontiguousarray(b, dtype=np.uint32).reshape(-1, NL)
+        out = np.empty_like(a)
+        self._check(self.L.gsn_fp768_binop_host(self._h, {"mul": 0, "add": 1, "sub": 2}[op], _ptr(out), _ptr(a), _ptr(b), a.shape[0]))
+        return out
+
+    # ---- 32-bit field
+    def best_fft32(self, a, omega, mod, inverse=False):
+        assert a.dtype == np.uint32 and a.flags["C_CONTIGUOUS"] and a.ndim == 1
+        self._check(self.L.gsn_ntt32_host(self._h, _ptr(a), a.shape[0], int(omega), int(mod), int(bool(inverse))))
+        return a
+
+    def ntt32(self, a, omega, mod, inverse=False):
+        out = np.ascontiguousarray(a, dtype=np.uint32).reshape(-1).copy()
+        return self.best_fft32(out, omega, mod, inverse)
+
+    def ntt32_device(self, dptr, n, omega, mod, inverse=False, batch=1, stream=None):
+        self._check(self.L.gsn_ntt32_device(self._h, C.c_void_p(dptr), int(n), int(batch), int(omega), int(mod), int(bool(inverse)),
+                                            C.c_void_p(stream or 0)))
+
+    def time_ntt32(self, dptr, n, omega, mod, inverse=False, batch=1, reps=10, rotate=1):
+        ms = (C.c_float * reps)()
+        self._check(self.L.gsn_ntt32_time_device(self._h, C.c_void_p(dptr), int(n), int(batch), int(omega), int(mod), int(bool(inverse)),
+                                                 reps, int(rotate), ms))
+        return list(ms)
+
+    # ---- measurement
+    def int32_issue_rates(self):
+        rates = (C.c_double * 5)()
+        sm, khz = C.c_int(), C.c_int()
+        self._check(self.L.gsn_int32_issue_rates(self._h, rates, C.byref(sm), C.byref(khz)))
+        names = ["imad_lo", "imad_hi", "imad_wide", "imad_wide_carry_chain", "imad_wide_plus_iadd3"]
+        return {"rates": dict(zip(names, rates)), "sm_count": sm.value, "sm_clock_khz": khz.value}
+
+
+def device_count():
+    L = _lib.load()
+    c = C.c_int()
+    rc = L.gsn_device_count(C.byref(c))
+    return c.value if rc == 0 else 0

@@ -1,0 +1,126 @@
+/* gpusnarks_b200.h -- C ABI of libgpusnarks_b200.so (B200 / sm_100a NTT library).
+ *
+ * This is the drop-in boundary for the reference's FFT hot path.  The reference has no C
+ * ABI: its entry point is a C++ template explicitly instantiated inside the CUDA static
+ * library,
+ *     template <typename FieldT> void best_fft(std::vector<FieldT>& a, const FieldT& omg);
+ *         (reference cuda/fft_kernel.h:24-25, defined cuda/fft_kernel.cu:117-147,
+ *          instantiated for fields::Scalar at cuda/fft_kernel.cu:150, called from
+ *          test/main.cpp:57)
+ * include/cuda/fft_kernel.h in this repository keeps that template (same name, same
+ * signature, same header path) and forwards to the functions below; INTEGRATION.md shows
+ * the binding.  Plain pointers and sizes only; no C++/torch types cross this boundary.
+ *
+ * Data format (identical to the reference): an element of the 768-bit field is 24
+ * little-endian uint32_t limbs (`fields::Scalar::im_rep`, reference cuda/device_field.h:75),
+ * elements are stored AoS, 96 bytes each, in Montgomery form (whatever domain the caller's
+ * operator* implies -- the transform is linear, so Montgomery in => Montgomery out).  Inputs
+ * must be canonical (< p); outputs are canonical.  An element of the 32-bit field is one
+ * uint32_t plain residue in [0, mod) (`dummy_fields::Field::im_rep`, reference
+ * fields/dummy_field.h:28).
+ *
+ * Semantics: out[i] = sum_j a[j] * omega^(i*j) mod p, natural order in and out, in place.
+ * inverse != 0 computes the same with omega^-1 and scales by n^-1 (libff convention).
+ *
+ * Every function returns GSN_OK (0) or a GSN_ERR_* code and never exits the process (the
+ * reference prints and exit(-1)s, cuda/fft_kernel.cu:34-39,137-142).  gsn_last_error()
+ * returns a thread-local message for the last failing call.
+ */
+#ifndef GPUSNARKS_B200_H
+#define GPUSNARKS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSN_OK 0
+#define GSN_ERR_INVALID_ARG 1   /* null pointer, bad enum */
+#define GSN_ERR_NOT_POW2 2      /* n is not a power of two (reference: assert(a.size()==CONSTRAINTS), fft_kernel.cu:123) */
+#define GSN_ERR_TOO_LARGE 3     /* n exceeds 2^two_adicity of the field, or device memory */
+#define GSN_ERR_BAD_OMEGA 4     /* omega is not a primitive n-th root of unity */
+#define GSN_ERR_CUDA 5          /* CUDA runtime error (message in gsn_last_error) */
+#define GSN_ERR_NO_DEVICE 6     /* no CUDA device: there is NO CPU fallback */
+#define GSN_ERR_BAD_MODULUS 7   /* 32-bit modulus not an odd prime < 2^31 */
+
+#define GSN_FIELD_MNT4753_FR 0  /* MNT4-753 scalar field (default; the north-star field) */
+#define GSN_FIELD_MNT4753_FQ 1  /* MNT4-753 base field = the reference's literal `_mod` (device_field.h:62-65) */
+
+#define GSN_FP768_LIMBS 24
+
+typedef struct gsn_ctx gsn_ctx;
+
+/* ---- context: owns a stream, the device workspace and the cached twiddle tables.
+ * Replaces the per-call cudaMalloc pair that the reference never frees (fft_kernel.cu:129-134).
+ * One context per host thread (calls on one context are serialised by an internal mutex). */
+int gsn_ctx_create(gsn_ctx **ctx, int device);
+int gsn_ctx_destroy(gsn_ctx *ctx);
+const char *gsn_last_error(void);
+/* choose the 768-bit modulus for this context's device (default GSN_FIELD_MNT4753_FR) */
+int gsn_set_field768(gsn_ctx *ctx, int field);
+/* drop cached plans (twiddle tables) and the workspace */
+int gsn_ctx_trim(gsn_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int gsn_launch_count(gsn_ctx *ctx, uint64_t *count);
+
+/* ---- 768-bit NTT.  Replaces best_fft<fields::Scalar> (reference cuda/fft_kernel.cu:117-150).
+ * host variant: `limbs` is host memory (n * 24 words), copied H2D, transformed, copied back
+ * (blocking, like the reference's two cudaMemcpy, fft_kernel.cu:131,144). */
+int gsn_ntt768_host(gsn_ctx *ctx, uint32_t *limbs, size_t n, const uint32_t omega[GSN_FP768_LIMBS], int inverse);
+/* device variant: `d_limbs` is device memory holding `batch` consecutive transforms of n
+ * elements; stream-ordered on `stream` (a cudaStream_t, NULL = the context's stream);
+ * returns after enqueueing. */
+int gsn_ntt768_device(gsn_ctx *ctx, uint32_t *d_limbs, size_t n, size_t batch, const uint32_t omega[GSN_FP768_LIMBS],
+                      int inverse, void *stream);
+/* Build (or fetch) the plan for (n, omega, inverse) without running it: twiddle tables are
+ * computed on the device once and cached.  Optional; the NTT calls do it on first use. */
+int gsn_ntt768_prepare(gsn_ctx *ctx, size_t n, size_t batch, const uint32_t omega[GSN_FP768_LIMBS], int inverse);
+
+/* Partial transform used by the multi-GPU four-step driver: `d_limbs` holds
+ * batch x n x 2^log_r elements indexed (batch | i | r); transforms along i only.
+ * pre_scale (device pointer, 24 limbs, may be NULL) multiplies every input element. */
+int gsn_ntt768_strided_device(gsn_ctx *ctx, uint32_t *d_limbs, size_t n, size_t batch, unsigned log_r,
+                              const uint32_t omega[GSN_FP768_LIMBS], int inverse, void *stream);
+/* d_limbs[i] *= omega^((row0 + i / cols) * (col0 + i % cols)) * (scale ? *scale : 1),
+ * i < rows*cols: the four-step twiddle between the column and the row transforms. */
+int gsn_fp768_twiddle_device(gsn_ctx *ctx, uint32_t *d_limbs, size_t rows, size_t cols, size_t row0, size_t col0,
+                             size_t n_total, const uint32_t omega[GSN_FP768_LIMBS], void *stream);
+
+/* ---- field arithmetic on arrays (parity tests of the device Montgomery code against the
+ * oracle; reference device_field_operators.h:190-214).  op: 0 mul (a*b*R^-1), 1 add, 2 sub. */
+int gsn_fp768_binop_host(gsn_ctx *ctx, int op, uint32_t *out, const uint32_t *a, const uint32_t *b, size_t count);
+
+/* ---- 32-bit NTT over Z/mod (mod an odd prime < 2^31 with n | mod-1).
+ * Replaces best_fft for the reference's 32-bit field sketch (fields/dummy_field.h:24-62). */
+int gsn_ntt32_host(gsn_ctx *ctx, uint32_t *a, size_t n, uint32_t omega, uint32_t mod, int inverse);
+int gsn_ntt32_device(gsn_ctx *ctx, uint32_t *d_a, size_t n, size_t batch, uint32_t omega, uint32_t mod, int inverse,
+                     void *stream);
+
+/* ---- host helpers (so callers need not link the CUDA runtime themselves) */
+int gsn_device_count(int *count);
+int gsn_host_alloc(void **ptr, size_t bytes);   /* pinned host memory */
+int gsn_host_free(void *ptr);
+int gsn_device_alloc(gsn_ctx *ctx, void **dptr, size_t bytes);
+int gsn_device_free(gsn_ctx *ctx, void *dptr);
+int gsn_memcpy_h2d(gsn_ctx *ctx, void *dptr, const void *hptr, size_t bytes);
+int gsn_memcpy_d2h(gsn_ctx *ctx, void *hptr, const void *dptr, size_t bytes);
+int gsn_ctx_synchronize(gsn_ctx *ctx);
+
+/* ---- measurement: INT32 multiply issue rates of the device (roofline denominator for the
+ * 768-bit path).  rates[k] = multiply instructions per second, chip wide, for
+ * k = 0 IMAD (mad.lo), 1 IMAD.HI (mad.hi), 2 IMAD.WIDE.U32 (mad.wide), 3 IMAD.WIDE.U32.X carry
+ * chains as issued by the Montgomery product, 4 IMAD.WIDE.U32 interleaved 1:1 with IADD3. */
+int gsn_int32_issue_rates(gsn_ctx *ctx, double rates[5], int *sm_count, int *sm_clock_khz);
+/* time `reps` back-to-back device transforms with CUDA events on the context's stream;
+ * ms_each[i] receives the i-th duration in milliseconds (data stays resident). */
+int gsn_ntt768_time_device(gsn_ctx *ctx, uint32_t *d_limbs, size_t n, size_t batch, const uint32_t omega[GSN_FP768_LIMBS],
+                           int inverse, int reps, float *ms_each);
+int gsn_ntt32_time_device(gsn_ctx *ctx, uint32_t *d_a, size_t n, size_t batch, uint32_t omega, uint32_t mod, int inverse,
+                          int reps, float *ms_each);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPUSNARKS_B200_H */
