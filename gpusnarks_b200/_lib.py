@@ -51,9 +51,9 @@ def load():
     L.gsn_memcpy_h2d.argtypes = [vp, vp, vp, sz]
     L.gsn_memcpy_d2h.argtypes = [vp, vp, vp, sz]
     L.gsn_ctx_synchronize.argtypes = [vp]
-    L.gsn_int32_issue_rates.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i), C.POINTER(i)]
+    L.gsn_int32_issue_rates.argtypes = [vp, C.POINTER(C.c_double), i, C.POINTER(i), C.POINTER(i), C.POINTER(i)]
     L.gsn_ntt768_time_device.argtypes = [vp, vp, sz, sz, u32p, i, i, C.POINTER(C.c_float)]
-    L.gsn_ntt32_time_device.argtypes = [vp, vp, sz, sz, u32, u32, i, i, i, C.POINTER(C.c_float)]
+    L.gsn_ntt32_time_device.argtypes = [vp, vp, sz, sz, u32, u32, i, i, C.POINTER(C.c_float)]
     for s in SYMBOLS:
         if s != "gsn_last_error":
             getattr(L, s).restype = i

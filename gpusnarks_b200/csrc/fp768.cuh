@@ -161,12 +161,12 @@ __device__ __forceinline__ void mont_mul_lazy_w(uint32_t *r, const uint32_t *a, 
         cios_step<false>(ev, od, a, b(i));
         cios_step<false>(od, ev, a, b(i + 1));
     }
-    // after an even number of steps `ev` is even-aligned again with ev[0] consumed:
-    // value = (ev >> 32) + od
-    r[0] = add_cc(ev[1], od[0]);
+    // The last step ran with the roles exchanged (even accumulator = `od`) and left its
+    // one-limb shift pending: value = (od >> 32) + ev.
+    r[0] = add_cc(od[1], ev[0]);
 #pragma unroll
-    for (int k = 1; k < NL - 1; ++k) r[k] = addc_cc(ev[k + 1], od[k]);
-    r[NL - 1] = addc(od[NL - 1], 0u);
+    for (int k = 1; k < NL - 1; ++k) r[k] = addc_cc(od[k + 1], ev[k]);
+    r[NL - 1] = addc(ev[NL - 1], 0u);
 }
 
 struct RegWords {

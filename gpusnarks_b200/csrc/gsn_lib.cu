@@ -20,7 +20,7 @@
 #include "../../include/gpusnarks_b200.h"
 #include "../../include/gsn_constants.h"
 #include "fp768.cuh"
-#include "host_fp768.h"
+#include "../../include/fields/fp768_host.h"
 #include "microbench.cuh"
 #include "ntt32.cuh"
 #include "ntt768.cuh"
@@ -501,25 +501,33 @@ int gsn_ctx_synchronize(gsn_ctx *ctx) {
 }
 
 // ---- INT32 issue-rate probe
-int gsn_int32_issue_rates(gsn_ctx *ctx, double rates[5], int *sm_count, int *sm_clock_khz) {
-    if (!ctx || !rates) return fail(GSN_ERR_INVALID_ARG, "null argument");
+}  // extern "C"
+
+template <int MODE>
+static void launch_probe(int blocks, int threads, cudaStream_t st, uint32_t *sink, uint32_t seed, int iters) {
+    gsn::int32_issue_probe<MODE><<<blocks, threads, 0, st>>>(sink, seed, iters);
+}
+
+extern "C" {
+
+int gsn_int32_issue_rates(gsn_ctx *ctx, double *rates, int max_modes, int *n_modes, int *sm_count, int *sm_clock_khz) {
+    if (!ctx || !rates || max_modes <= 0) return fail(GSN_ERR_INVALID_ARG, "null argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->device));
     DevBuf sink;
     int rc;
     if ((rc = dev_alloc(sink, 256))) return rc;
     const int iters = 8192, blocks = ctx->sm_count * 8, threads = 256;
-    for (int mode = 0; mode < 5; ++mode) {
+    typedef void (*launch_fn)(int, int, cudaStream_t, uint32_t *, uint32_t, int);
+    static const launch_fn fns[gsn::INT32_PROBE_MODES] = {launch_probe<0>, launch_probe<1>, launch_probe<2>, launch_probe<3>,
+                                                         launch_probe<4>, launch_probe<5>, launch_probe<6>, launch_probe<7>,
+                                                         launch_probe<8>, launch_probe<9>, launch_probe<10>, launch_probe<11>};
+    const int modes = std::min(max_modes, gsn::INT32_PROBE_MODES);
+    for (int mode = 0; mode < modes; ++mode) {
         float best = 1e30f;
         for (int rep = 0; rep < 4; ++rep) {
             CU(cudaEventRecord(ctx->ev0, ctx->stream));
-            switch (mode) {
-                case 0: gsn::int32_issue_probe<0><<<blocks, threads, 0, ctx->stream>>>((uint32_t *)sink.p, 12345u + rep, iters); break;
-                case 1: gsn::int32_issue_probe<1><<<blocks, threads, 0, ctx->stream>>>((uint32_t *)sink.p, 12345u + rep, iters); break;
-                case 2: gsn::int32_issue_probe<2><<<blocks, threads, 0, ctx->stream>>>((uint32_t *)sink.p, 12345u + rep, iters); break;
-                case 3: gsn::int32_issue_probe<3><<<blocks, threads, 0, ctx->stream>>>((uint32_t *)sink.p, 12345u + rep, iters); break;
-                default: gsn::int32_issue_probe<4><<<blocks, threads, 0, ctx->stream>>>((uint32_t *)sink.p, 12345u + rep, iters); break;
-            }
+            fns[mode](blocks, threads, ctx->stream, (uint32_t *)sink.p, 12345u + rep, iters);
             ctx->launches++;
             CU(cudaEventRecord(ctx->ev1, ctx->stream));
             CU(cudaEventSynchronize(ctx->ev1));
@@ -531,6 +539,7 @@ int gsn_int32_issue_rates(gsn_ctx *ctx, double rates[5], int *sm_count, int *sm_
         rates[mode] = ops / (best * 1e-3);
     }
     CU(cudaGetLastError());
+    if (n_modes) *n_modes = modes;
     if (sm_count) *sm_count = ctx->sm_count;
     if (sm_clock_khz) { int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device); *sm_clock_khz = khz; }
     return GSN_OK;

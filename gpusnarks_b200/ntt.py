@@ -140,19 +140,21 @@ class Context:
         self._check(self.L.gsn_ntt32_device(self._h, C.c_void_p(dptr), int(n), int(batch), int(omega), int(mod), int(bool(inverse)),
                                             C.c_void_p(stream or 0)))
 
-    def time_ntt32(self, dptr, n, omega, mod, inverse=False, batch=1, reps=10, rotate=1):
+    def time_ntt32(self, dptr, n, omega, mod, inverse=False, batch=1, reps=10):
         ms = (C.c_float * reps)()
         self._check(self.L.gsn_ntt32_time_device(self._h, C.c_void_p(dptr), int(n), int(batch), int(omega), int(mod), int(bool(inverse)),
-                                                 reps, int(rotate), ms))
+                                                 reps, ms))
         return list(ms)
 
     # ---- measurement
     def int32_issue_rates(self):
-        rates = (C.c_double * 5)()
-        sm, khz = C.c_int(), C.c_int()
-        self._check(self.L.gsn_int32_issue_rates(self._h, rates, C.byref(sm), C.byref(khz)))
-        names = ["imad_lo", "imad_hi", "imad_wide", "imad_wide_carry_chain", "imad_wide_plus_iadd3"]
-        return {"rates": dict(zip(names, rates)), "sm_count": sm.value, "sm_clock_khz": khz.value}
+        rates = (C.c_double * 16)()
+        nm, sm, khz = C.c_int(), C.c_int(), C.c_int()
+        self._check(self.L.gsn_int32_issue_rates(self._h, rates, 16, C.byref(nm), C.byref(sm), C.byref(khz)))
+        names = ["imad_lo", "imad_hi_invariant", "imad_wide", "imad_wide_x_short_chain", "imad_wide_with_iadd3", "imad_hi",
+                 "imad_lo_carry_chain", "imad_hi_carry_chain", "iadd3_x_chain", "imad_wide_x_long_chain", "imad_lo_hi_pairs",
+                 "imad_wide_variant"]
+        return {"rates": {names[k]: rates[k] for k in range(nm.value)}, "sm_count": sm.value, "sm_clock_khz": khz.value}
 
 
 def device_count():

@@ -1,4 +1,4 @@
-// host_fp768.h -- host-side 768-bit Montgomery arithmetic used by the library's planner
+// fields/fp768_host.h -- host-side 768-bit Montgomery arithmetic: used by the library planner
 // (omega validation, omega^-1, n^-1).  Product code: independent of oracle/ (which is test
 // infrastructure) -- 12 x 64-bit limbs with unsigned __int128, where the oracle uses the
 // reference's 24 x 32-bit CIOS loop nest.
