@@ -1,0 +1,344 @@
+#!/usr/bin/env python3
+"""bench.py -- the hot-path benchmark of gpusnarks_b200 (contract: see the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--log-n L]
+
+Metric (BASELINE.json): 768-bit NTT butterflies/s, butterflies = (n/2) * log2(n) per transform.
+  N = 1   workload = BASELINE.json configs[2]: MNT4-753 Fr forward NTT, n = 2^20, one B200.
+  N > 1   workload = configs[3]: MNT4-753 Fr forward NTT, n = 2^24, four-step sharded across
+          the N GPUs with one NCCL all-to-all (strong scaling: the same transform on more GPUs).
+A "step" is one whole transform of synthetic random field elements.
+  value   device-resident: inputs already in HBM, K steps between barrier + synchronize,
+          CUDA events on the launching stream, max over ranks.
+  e2e     the same transform through the host-pointer C ABI call (gsn_ntt768_host): pinned
+          host buffer -> H2D -> transform -> D2H inside the timed region, every step.
+  roofline  the dominant kernel (ntt768_pass) against the INT32 multiply issue peak measured
+          in this same process (gsn_int32_issue_rates, plain IMAD.WIDE.U32), algorithmic work
+          = 1176 wide MACs per butterfly; HBM figures given alongside.
+  cpu_baseline  the reference's own host FFT (oracle/_ref/libref_verbatim.so, compiled from
+          /root/reference, test/fft_host.h via the host half of test/main.cpp:64-76) timed on
+          this box's cores on a bounded sample.
+--impl reference times only that CPU reference (rank 0) on the same config and metric.
+"""
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MACS_PER_BUTTERFLY = 1176  # 2*24^2 + 24
+
+
+def butterflies(logn):
+    return (1 << logn) // 2 * logn
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as f:
+            for line in f:
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    mx.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(names, parts[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        os.unlink(self.path)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ CPU reference
+def _ref_lib():
+    """the reference compiled from /root/reference (kind 'reference'), else the oracle port"""
+    u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_verbatim.so")
+    if os.path.exists(path):
+        L = C.CDLL(path)
+        L.ref_fft_scalar.argtypes = [u32p, C.c_size_t, u32p, C.c_int, C.c_int]
+        L.ref_fft_scalar.restype = C.c_double
+        return "reference", lambda a, n, w, lc, thr: L.ref_fft_scalar(a, n, w, lc, thr)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    lib = O.lib()
+
+    def run(a, n, w, lc, thr):
+        lib.oracle_set_threads(thr)
+        return lib.oracle_time_fft768(a, n, w, lc)
+    return "port", run
+
+
+def synth_host(n, seed):
+    """seeded canonical elements: 24 random limbs, top limb masked to 16 bits (< 2^752 < r)"""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    a = rng.integers(0, 1 << 32, size=(n, 24), dtype=np.uint64).astype(np.uint32)
+    a[:, 23] &= 0xFFFF
+    return a
+
+
+def cpu_reference_run(sample_logn, steps, warmup):
+    from gpusnarks_b200 import field as F
+    kind, run = _ref_lib()
+    cores = os.cpu_count() or 1
+    log_cpus = int(math.log2(cores))
+    n = 1 << sample_logn
+    a = synth_host(n, 1)
+    w = F.root_of_unity768(n)
+    times = []
+    for i in range(warmup + steps):
+        buf = a.copy()
+        t = run(buf, n, w, log_cpus, cores)
+        if i >= warmup:
+            times.append(t)
+    sec = float(np.mean(times))
+    sample = (f"one forward host FFT (reference test/fft_host.h _basic_parallel_radix2_FFT_inner<fields::Scalar>, log_cpus={log_cpus}, "
+              f"{cores} OpenMP threads, g++ -O2) of n=2^{sample_logn} random elements per step; mean of {steps} step(s)")
+    return {"value": butterflies(sample_logn) / sec, "unit": "butterflies/s", "cores": cores, "kind": kind, "sample": sample,
+            "seconds_per_step": sec}
+
+
+# ------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log-n", type=int, default=0, help="override the transform size (default 20 at N=1, 24 at N>1)")
+    ap.add_argument("--cpu-sample-log-n", type=int, default=18)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    N = max(args.gpus, 1)
+    logn = args.log_n or (20 if N == 1 else 24)
+    workload = (f"MNT4-753 Fr (768-bit) forward NTT n=2^{logn} on 1xB200" if N == 1 else
+                f"MNT4-753 Fr (768-bit) forward NTT n=2^{logn}, four-step sharded across {N}xB200, NCCL all-to-all")
+    config = {"workload": workload, "log_n": logn, "field": "MNT4-753 Fr", "element_bytes": 96,
+              "l2": "working set (data + workspace + twiddle table, 3 x n x 96 B) exceeds the 126 MB L2; no flush needed"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sl = min(args.cpu_sample_log_n, logn)
+        steps = max(1, min(args.steps, 3))  # bounded: each step is seconds of CPU work
+        cb = cpu_reference_run(sl, steps, min(args.warmup, 1))
+        line = {"impl": "reference", "metric": "768-bit NTT butterflies/s", "value": cb["value"], "unit": "butterflies/s", "n_gpus": N,
+                "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": cb["seconds_per_step"] * 1e3, "higher_is_better": True,
+                "scaling": "strong" if N > 1 else "weak", "vs_baseline": None, "dtype": "u32x24 (768-bit Montgomery, integer)",
+                "data": "synthetic", "config": config, "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "butterflies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import gpusnarks_b200 as g
+    from gpusnarks_b200 import field as F
+    from gpusnarks_b200 import fourstep
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; gpusnarks_b200 has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == N or world == 1, f"--gpus {N} but WORLD_SIZE={world}"
+
+    ctx = g.Context(local_rank)
+    stream = torch.cuda.Stream(dev)  # a real (non-default) stream: the library launches on it, torch events time it
+    torch.cuda.set_stream(stream)
+    n = 1 << logn
+    omega = F.root_of_unity768(n)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1 + rank)
+
+    def synth(shape):
+        t = torch.randint(-(1 << 31), (1 << 31) - 1, shape, dtype=torch.int32, device=dev, generator=gen)
+        t[..., 23] &= 0xFFFF
+        return t
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    rates = ctx.int32_issue_rates() if rank == 0 else None
+    launches0 = ctx.launch_count()
+
+    if world == 1:
+        data = synth((n, 24))
+        ctx.prepare768(n, omega)
+
+        def step():
+            ctx.ntt768_device(data.data_ptr(), n, omega, stream=stream.cuda_stream)
+        local_bytes = n * 96
+        passes = max(1, -(-logn // 10))
+        kernels_per_step = passes
+    else:
+        plan = fourstep.FourStepNTT768(fourstep.CudaBackend(ctx, dev), logn, omega, directions=("forward",))
+        data = synth(plan.column_block_shape())
+        state = {"x": data}
+
+        def step():
+            # forward maps column-block -> row-block; feed the output shape back by regenerating a view
+            state["y"] = plan.forward(state["x"])
+        local_bytes = data.numel() * 4
+        kernels_per_step = None
+
+    sampler = ClockSampler(local_rank)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    launches1 = ctx.launch_count()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches2 = ctx.launch_count()
+
+    # ---- e2e: host-pointer public API, pinned host memory, H2D + transform + D2H per step
+    e2e_steps = max(3, min(args.steps, 10))
+    if world == 1:
+        host = torch.empty((n, 24), dtype=torch.int32, pin_memory=True)
+        host.copy_(data)
+        host_np = host.numpy().view(np.uint32)
+        ctx.best_fft768(host_np, omega)  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ctx.best_fft768(host_np, omega)
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        h2d = d2h = n * 96
+    else:
+        shard = torch.empty(plan.column_block_shape(), dtype=torch.int32, pin_memory=True)
+        shard.copy_(data)
+        out_host = torch.empty(plan.row_block_shape(), dtype=torch.int32, pin_memory=True)
+        dbuf = torch.empty_like(data)
+
+        def e2e_step():
+            dbuf.copy_(shard, non_blocking=True)
+            y = plan.forward(dbuf)
+            out_host.copy_(y, non_blocking=True)
+            torch.cuda.synchronize(dev)
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        h2d = d2h = local_bytes
+    clocks = sampler.stop()
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([ms_total, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, e2e_ms = float(t[0]), float(t[1])
+    ms_step = ms_total / args.steps
+    bf = butterflies(logn)
+    value = bf / (ms_step * 1e-3)
+
+    if rank == 0:
+        p_mac = rates["rates"]["imad_wide"]
+        achieved = value * MACS_PER_BUTTERFLY / N  # per GPU
+        passes = max(1, -(-logn // 10)) if world == 1 else None
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        # algorithmic bytes per transform: each pass reads and writes every element once
+        # (+ one twiddle-table read per pass boundary)
+        if world == 1:
+            alg_bytes = (2 * passes + (passes - 1)) * n * 96
+        else:
+            alg_bytes = None
+        roofline = {
+            "kernel": "gsn::ntt768_pass<256,2>",
+            "bound": "int32_mul",
+            "achieved": achieved / 1e12, "peak": p_mac / 1e12, "unit": "T wide-MAC/s (32x32+64 IMAD.WIDE.U32)",
+            "frac": achieved / p_mac,
+            "algorithmic_macs_per_butterfly": MACS_PER_BUTTERFLY,
+            "peak_source": "gsn_int32_issue_rates (plain IMAD.WIDE.U32, no carry chain) measured in this process",
+            "int32_issue_rates_per_s": rates["rates"],
+            "launches_per_step": kernels_per_step,
+            "avg_launch_ms": (ms_step / kernels_per_step) if kernels_per_step else None,
+            "traffic": None,
+            "hbm": {"algorithmic_bytes_per_step": alg_bytes, "achieved_gbs": (alg_bytes / (ms_step * 1e-3) / 1e9) if alg_bytes else None,
+                    "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650"},
+        }
+        line = {
+            "metric": "768-bit NTT butterflies/s", "value": value, "unit": "butterflies/s", "n_gpus": N, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong" if N > 1 else "weak", "vs_baseline": None,
+            "dtype": "u32x24 (768-bit Montgomery, integer)", "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": bf / (e2e_ms * 1e-3), "unit": "butterflies/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms, "steps": e2e_steps, "api": "gsn_ntt768_host (pinned host buffer)" if world == 1 else
+                    "pinned shard -> H2D -> FourStepNTT768.forward -> D2H, per rank"},
+            "gpu_launches": launches2 - launches1,
+            "roofline": roofline,
+        }
+        if N == 1:
+            try:
+                line["cpu_baseline"] = cpu_reference_run(min(args.cpu_sample_log_n, logn), 1, 0)
+            except Exception as e:  # the bench line must still print
+                line["cpu_baseline"] = {"error": str(e)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -60,7 +60,8 @@ struct DevBuf {
 struct Plan768 {
     int field = 0;
     uint32_t logn = 0;
-    int inverse = 0;
+    int inverse = 0;              // use omega^-1
+    int scale = 0;                // fold n^-1 into the transform
     uint32_t omega[24];           // as passed by the caller (forward root)
     std::vector<uint32_t> digits; // l_1..l_P
     uint32_t lmax = 0;
@@ -157,9 +158,9 @@ int validate_omega768(gsn_ctx *ctx, const uint32_t *omega, uint32_t logn) {
     return GSN_OK;
 }
 
-int get_plan768(gsn_ctx *ctx, uint32_t logn, const uint32_t *omega, int inverse, Plan768 **out) {
+int get_plan768(gsn_ctx *ctx, uint32_t logn, const uint32_t *omega, int inverse, int scale, Plan768 **out) {
     for (auto &pl : ctx->plans768)
-        if (pl->field == ctx->field && pl->logn == logn && pl->inverse == (inverse != 0) && memcmp(pl->omega, omega, 96) == 0) {
+        if (pl->field == ctx->field && pl->logn == logn && pl->inverse == (inverse != 0) && pl->scale == (scale != 0) && memcmp(pl->omega, omega, 96) == 0) {
             *out = pl.get();
             return GSN_OK;
         }
@@ -171,6 +172,7 @@ int get_plan768(gsn_ctx *ctx, uint32_t logn, const uint32_t *omega, int inverse,
     pl->field = ctx->field;
     pl->logn = logn;
     pl->inverse = inverse != 0;
+    pl->scale = scale != 0;
     memcpy(pl->omega, omega, 96);
     pl->digits = plan_digits(logn, MAX_PASS_LOG);
     pl->lmax = *std::max_element(pl->digits.begin(), pl->digits.end());
@@ -182,8 +184,8 @@ int get_plan768(gsn_ctx *ctx, uint32_t logn, const uint32_t *omega, int inverse,
     // effective root (omega or omega^-1 = omega^(n-1)) and n^-1, Montgomery form, on the host
     uint64_t w_eff[12], n_inv[12];
     memcpy(w_eff, omega, 96);
-    if (inverse) {
-        ctx->hf.pow(w_eff, w_eff, n - 1);
+    if (inverse) ctx->hf.pow(w_eff, w_eff, n - 1);
+    if (scale) {
         memcpy(n_inv, ctx->hf.r1, 96);
         for (uint32_t i = 0; i < logn; ++i) ctx->hf.halve(n_inv, n_inv);
     }
@@ -191,7 +193,7 @@ int get_plan768(gsn_ctx *ctx, uint32_t logn, const uint32_t *omega, int inverse,
     DevBuf d_w, d_ninv, t_lo, t_hi;
     if ((rc = dev_alloc(d_w, 96))) return rc;
     CU(cudaMemcpyAsync(d_w.p, w_eff, 96, cudaMemcpyHostToDevice, st));
-    if (inverse) {
+    if (scale) {
         if ((rc = dev_alloc(d_ninv, 96))) return rc;
         CU(cudaMemcpyAsync(d_ninv.p, n_inv, 96, cudaMemcpyHostToDevice, st));
     }
@@ -214,7 +216,7 @@ int get_plan768(gsn_ctx *ctx, uint32_t logn, const uint32_t *omega, int inverse,
             uint32_t logN = 0;
             for (size_t i = q - 1; i < P; ++i) logN += pl->digits[i];
             const uint32_t rest_bits = logN - pl->digits[q - 1];
-            if (q == 1 && inverse) {
+            if (q == 1 && scale) {
                 const uint64_t cnt = 1ull << lo_bits;
                 gsn::scale_table768<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>((uint32_t *)t_lo.p, (const uint32_t *)t_lo.p, (const uint32_t *)d_ninv.p, cnt);
                 ctx->launches++;
@@ -227,7 +229,7 @@ int get_plan768(gsn_ctx *ctx, uint32_t logn, const uint32_t *omega, int inverse,
                                                                                 logN, rest_bits, logn - logN, lo_bits);
             ctx->launches++;
         }
-    } else if (inverse) {
+    } else if (scale) {
         pl->pre[0] = std::make_unique<DevBuf>();
         if ((rc = dev_alloc(*pl->pre[0], 96))) return rc;
         CU(cudaMemcpyAsync(pl->pre[0]->p, n_inv, 96, cudaMemcpyHostToDevice, st));
@@ -240,7 +242,7 @@ int get_plan768(gsn_ctx *ctx, uint32_t logn, const uint32_t *omega, int inverse,
     return GSN_OK;
 }
 
-int launch_ntt768(gsn_ctx *ctx, Plan768 *pl, uint32_t *d_data, size_t batch, uint32_t log_r, cudaStream_t st) {
+int launch_ntt768(gsn_ctx *ctx, Plan768 *pl, uint32_t *d_data, size_t batch, uint32_t log_r, const uint32_t *ext_pre, cudaStream_t st) {
     const size_t P = pl->digits.size();
     const uint64_t total = (uint64_t)batch << (pl->logn + log_r);
     uint32_t v2 = 0;
@@ -265,6 +267,7 @@ int launch_ntt768(gsn_ctx *ctx, Plan768 *pl, uint32_t *d_data, size_t batch, uin
         g.log_l = pl->digits[q];
         g.log_s = below;
         g.log_r = log_r;
+        g.pre_shift = log_r;
         g.log_tile = log_tile;
         g.wloc_shift = pl->lmax - pl->digits[q];
         g.final_natural = q + 1 == P;
@@ -274,13 +277,19 @@ int launch_ntt768(gsn_ctx *ctx, Plan768 *pl, uint32_t *d_data, size_t batch, uin
         g.logn = pl->logn;
         g.has_pre = pl->pre[q] != nullptr;
         g.pre_mask = pl->pre_mask[q];
+        const uint32_t *pre = g.has_pre ? (const uint32_t *)pl->pre[q]->p : nullptr;
+        if (q == 0 && ext_pre) {  // caller-supplied table indexed by the element index (four-step twiddles)
+            g.has_pre = 1;
+            g.pre_mask = ~0ull;
+            g.pre_shift = 0;
+            pre = ext_pre;
+        }
         // pass 1 reads the caller's buffer, the last pass writes it; middle passes run in
         // place in the workspace (a tile reads and writes the same index set).
         const uint32_t *src = q == 0 ? d_data : work;
         uint32_t *dst = (q + 1 == P) ? d_data : work;
         const size_t smem = ((size_t)1 << log_tile) * gsn::SMEM_PITCH4 * 16;
-        kern<<<(unsigned)(total >> log_tile), NTT768_THREADS, smem, st>>>(src, dst, (const uint32_t *)pl->wloc.p,
-                                                                           g.has_pre ? (const uint32_t *)pl->pre[q]->p : nullptr, g);
+        kern<<<(unsigned)(total >> log_tile), NTT768_THREADS, smem, st>>>(src, dst, (const uint32_t *)pl->wloc.p, pre, g);
         ctx->launches++;
     }
     CU(cudaGetLastError());
@@ -379,21 +388,30 @@ int gsn_ntt768_prepare(gsn_ctx *ctx, size_t n, size_t batch, const uint32_t *ome
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->device));
     Plan768 *pl;
-    if ((rc = get_plan768(ctx, ilog2(n), omega, inverse, &pl))) return rc;
+    if ((rc = get_plan768(ctx, ilog2(n), omega, inverse, inverse, &pl))) return rc;
     if (pl->digits.size() > 1) return ensure_work(ctx, (size_t)batch * n * 96);
     return GSN_OK;
 }
 
-int gsn_ntt768_strided_device(gsn_ctx *ctx, uint32_t *d_limbs, size_t n, size_t batch, unsigned log_r, const uint32_t *omega,
-                              int inverse, void *stream) {
+int gsn_ntt768_device_ex(gsn_ctx *ctx, uint32_t *d_limbs, size_t n, size_t batch, unsigned log_r, const uint32_t *omega,
+                         unsigned flags, const uint32_t *d_pre_table, void *stream) {
     if (!ctx || !d_limbs || !omega) return fail(GSN_ERR_INVALID_ARG, "null argument");
     int rc = check_n(n, batch);
     if (rc) return rc;
+    if (log_r > 40) return fail(GSN_ERR_INVALID_ARG, "log_r = %u", log_r);
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->device));
     Plan768 *pl;
-    if ((rc = get_plan768(ctx, ilog2(n), omega, inverse, &pl))) return rc;
-    return launch_ntt768(ctx, pl, d_limbs, batch, log_r, stream ? (cudaStream_t)stream : ctx->stream);
+    const int inv = (flags & GSN_FLAG_INVERSE_ROOT) != 0, scale = inv && !(flags & GSN_FLAG_NO_SCALE);
+    if (d_pre_table && scale && n <= 1024)
+        return fail(GSN_ERR_INVALID_ARG, "a pre-twiddle table and n^-1 scaling cannot share a one-pass transform: fold the scale into the table and pass GSN_FLAG_NO_SCALE");
+    if ((rc = get_plan768(ctx, ilog2(n), omega, inv, scale, &pl))) return rc;
+    return launch_ntt768(ctx, pl, d_limbs, batch, log_r, d_pre_table, stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+int gsn_ntt768_strided_device(gsn_ctx *ctx, uint32_t *d_limbs, size_t n, size_t batch, unsigned log_r, const uint32_t *omega,
+                              int inverse, void *stream) {
+    return gsn_ntt768_device_ex(ctx, d_limbs, n, batch, log_r, omega, inverse ? GSN_FLAG_INVERSE_ROOT : 0, nullptr, stream);
 }
 
 int gsn_ntt768_device(gsn_ctx *ctx, uint32_t *d_limbs, size_t n, size_t batch, const uint32_t *omega, int inverse, void *stream) {
@@ -452,10 +470,46 @@ int gsn_fp768_binop_host(gsn_ctx *ctx, int op, uint32_t *out, const uint32_t *a,
     return GSN_OK;
 }
 
-int gsn_fp768_twiddle_device(gsn_ctx *ctx, uint32_t *d_limbs, size_t rows, size_t cols, size_t row0, size_t col0, size_t n_total,
-                             const uint32_t *omega, void *stream) {
-    (void)ctx; (void)d_limbs; (void)rows; (void)cols; (void)row0; (void)col0; (void)n_total; (void)omega; (void)stream;
-    return fail(GSN_ERR_INVALID_ARG, "gsn_fp768_twiddle_device: not built yet");
+int gsn_fourstep_table768(gsn_ctx *ctx, uint32_t *d_table, size_t rows, size_t cols, size_t row0, size_t col0, size_t n_total,
+                          const uint32_t *omega, unsigned flags, void *stream) {
+    if (!ctx || !d_table || !omega) return fail(GSN_ERR_INVALID_ARG, "null argument");
+    if (!is_pow2(n_total) || rows == 0 || cols == 0) return fail(GSN_ERR_NOT_POW2, "n_total = %zu", n_total);
+    const uint32_t logn = ilog2(n_total);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    if ((int)logn > ctx->two_adicity) return fail(GSN_ERR_TOO_LARGE, "n = 2^%u exceeds the field's 2-adicity %d", logn, ctx->two_adicity);
+    int rc = validate_omega768(ctx, omega, logn);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    uint64_t w_eff[12], sc[12];
+    memcpy(w_eff, omega, 96);
+    if (flags & GSN_FLAG_INVERSE_ROOT) ctx->hf.pow(w_eff, w_eff, n_total - 1);
+    const bool scale = (flags & GSN_FLAG_SCALE_TABLE) != 0;
+    if (scale) {
+        memcpy(sc, ctx->hf.r1, 96);
+        for (uint32_t i = 0; i < logn; ++i) ctx->hf.halve(sc, sc);
+    }
+    const uint32_t lo_bits = (logn + 1) / 2;
+    DevBuf d_w, d_sc, t_lo, t_hi;
+    if ((rc = dev_alloc(d_w, 96)) || (rc = dev_alloc(t_lo, (1ull << lo_bits) * 96)) || (rc = dev_alloc(t_hi, (n_total >> lo_bits) * 96))) return rc;
+    CU(cudaMemcpyAsync(d_w.p, w_eff, 96, cudaMemcpyHostToDevice, st));
+    gsn::pow_table768<<<(unsigned)(((1ull << lo_bits) + 127) / 128), 128, 0, st>>>((uint32_t *)t_lo.p, (const uint32_t *)d_w.p, 1ull << lo_bits, 1);
+    gsn::pow_table768<<<(unsigned)(((n_total >> lo_bits) + 127) / 128), 128, 0, st>>>((uint32_t *)t_hi.p, (const uint32_t *)d_w.p, n_total >> lo_bits, 1ull << lo_bits);
+    ctx->launches += 2;
+    if (scale) {
+        if ((rc = dev_alloc(d_sc, 96))) return rc;
+        CU(cudaMemcpyAsync(d_sc.p, sc, 96, cudaMemcpyHostToDevice, st));
+        const uint64_t cnt = 1ull << lo_bits;
+        gsn::scale_table768<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>((uint32_t *)t_lo.p, (const uint32_t *)t_lo.p, (const uint32_t *)d_sc.p, cnt);
+        ctx->launches++;
+    }
+    const uint64_t cnt = (uint64_t)rows * cols;
+    gsn::build_fourstep768<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>(d_table, (const uint32_t *)t_lo.p, (const uint32_t *)t_hi.p, rows, cols, row0,
+                                                                           col0, logn, lo_bits);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));  // the temporaries above are freed on return
+    return GSN_OK;
 }
 
 // ---- helpers

@@ -49,7 +49,7 @@ ntt32_pass(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, const u
         else { slot = e >> lq; j = e & Lm1; }
         const uint64_t gi = elem_index(g, sub0 + slot, j);
         uint32_t x = src[gi];
-        if (g.has_pre) x = mulmod_shoup(x, __ldg(pre_tw + ((gi >> g.log_r) & g.pre_mask)), p);
+        if (g.has_pre) x = mulmod_shoup(x, __ldg(pre_tw + ((gi >> g.pre_shift) & g.pre_mask)), p);
         tile32[(slot << lq) | (lq ? (__brev(j) >> (32 - lq)) : 0u)] = x;
     }
     __syncthreads();

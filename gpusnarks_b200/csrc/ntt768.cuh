@@ -36,7 +36,8 @@ constexpr int SMEM_PITCH4 = 7;  // uint4 per element in shared memory (112 B)
 struct PassGeom {
     uint32_t log_l;          // stages of this pass (digit width)
     uint32_t log_s;          // log2 stride (elements) of this digit
-    uint32_t log_r;          // log2 inner stride (pre-twiddle index = (g >> log_r) & pre_mask)
+    uint32_t log_r;          // log2 inner stride (elements below the transform index)
+    uint32_t pre_shift;      // pre-twiddle index = (element index >> pre_shift) & pre_mask
     uint32_t log_tile;       // log2 elements per CTA tile (>= log_l)
     uint32_t wloc_shift;     // local table index = (jj << (log_l - s)) << wloc_shift
     uint32_t final_natural;  // last pass: write digits reversed
@@ -126,7 +127,7 @@ ntt768_pass(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, const 
                 const uint32_t slot = b >> lq;
                 const uint32_t j = lq ? (__brev(b & Lm1) >> (32 - lq)) : 0u;
                 const uint64_t gi = elem_index(g, sub0 + slot, j);
-                wp = pre_tw + ((gi >> g.log_r) & g.pre_mask) * NL;
+                wp = pre_tw + ((gi >> g.pre_shift) & g.pre_mask) * NL;
             } else {
                 const uint32_t m = 1u << (ph - 1);
                 const uint32_t jj = b & (m - 1);
@@ -218,6 +219,21 @@ __global__ void build_pretw768(uint32_t *out, const uint32_t *t_lo, const uint32
     load_elem(b, t_hi + (e >> lo_bits) * NL);
     mont_mul(r, a, b);
     store_elem(out + idx * NL, r);
+}
+
+// Four-step (Bailey) twiddles of one shard: out[r * cols + c] = w_n^((row0 + r) * (col0 + c) mod n)
+// from the two-level tables t_lo[e] = w^e (e < 2^lo_bits), t_hi[e] = w^(e << lo_bits).
+__global__ void build_fourstep768(uint32_t *out, const uint32_t *t_lo, const uint32_t *t_hi, uint64_t rows, uint64_t cols,
+                                  uint64_t row0, uint64_t col0, uint32_t logn, uint32_t lo_bits) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * cols) return;
+    const uint64_t r = idx / cols, c = idx - r * cols;
+    const uint64_t e = ((row0 + r) * (col0 + c)) & ((1ull << logn) - 1);
+    uint32_t a[NL], b[NL], o[NL];
+    load_elem(a, t_lo + (e & ((1ull << lo_bits) - 1)) * NL);
+    load_elem(b, t_hi + (e >> lo_bits) * NL);
+    mont_mul(o, a, b);
+    store_elem(out + idx * NL, o);
 }
 
 // out[i] = a[i] * s   (canonical); used to fold n^-1 into a table

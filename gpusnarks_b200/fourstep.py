@@ -1,0 +1,127 @@
+"""Four-step (Bailey) 768-bit NTT sharded across the GPUs of one box, one process per GPU.
+
+Same decomposition as the reference's host "parallel FFT" (`_basic_parallel_radix2_FFT_inner`,
+reference test/fft_host.h:56-117: short-side DFTs times omega^(j*i), row FFTs, transposed
+write-out), with the short side done as a fast NTT and the shared-memory `tmp` matrix replaced
+by ONE all-to-all over NVLink (torch.distributed / NCCL):
+
+    n = n1 * n2,  input index i = i1*n2 + i2,  output index k = k1 + n1*k2
+    1. column NTTs   rank g owns columns i2 in [g*C, (g+1)*C), C = n2/G: n1-point transforms
+                     along i1 with root omega^n2                      (gsn_ntt768_device_ex, log_r)
+    2. all-to-all    rank g sends rows k1 in [h*R, (h+1)*R), R = n1/G, to rank h
+    3. row NTTs      rank h owns rows k1: multiply by omega^(k1*i2) (table fused into the first
+                     pass) and transform along i2 with root omega^n1
+
+Layouts (both are views of the natural-order vector, no data is ever bit-reversed):
+    column-block  x[i1, c]  = a[i1*n2 + g*C + c]            shape (n1, C, 24)   forward input
+    row-block     y[r, k2]  = A[(h*R + r) + n1*k2]          shape (R, n2, 24)   forward output
+The inverse runs the three steps backwards (inverse row NTTs, all-to-all, conjugate twiddles
+* n^-1 fused into the inverse column NTTs) and maps row-block back to column-block.
+
+The numerical work is done by a backend object; the product backend is `CudaBackend` (the C
+ABI).  tests/ inject a CPU backend to exercise the exchange logic under gloo.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import field as F
+
+
+def _ilog2(x):
+    assert x > 0 and x & (x - 1) == 0, f"{x} is not a power of two"
+    return x.bit_length() - 1
+
+
+class CudaBackend:
+    """Local transforms through libgpusnarks_b200.so on torch-owned device memory."""
+
+    def __init__(self, ctx, device):
+        self.ctx = ctx
+        self.device = device
+
+    def _stream(self):
+        # torch's legacy default stream has handle 0, which the C ABI reads as "use the context's
+        # own stream"; pass cudaStreamLegacy (0x1) instead so the kernels stay ordered with torch ops
+        return torch.cuda.current_stream(self.device).cuda_stream or 1
+
+    def ntt(self, t, n, batch, log_r, omega, inverse_root=False, no_scale=False, pre_table=None):
+        assert t.is_cuda and t.is_contiguous() and t.dtype == torch.int32
+        self.ctx.ntt768_device_ex(t.data_ptr(), n, omega, batch=batch, log_r=log_r, inverse_root=inverse_root, no_scale=no_scale,
+                                  pre_table=pre_table.data_ptr() if pre_table is not None else None, stream=self._stream())
+
+    def table(self, rows, cols, row0, col0, n_total, omega, inverse_root=False, scale=False):
+        t = torch.empty((rows, cols, F.NL), dtype=torch.int32, device=self.device)
+        self.ctx.fourstep_table768(t.data_ptr(), rows, cols, row0, col0, n_total, omega, inverse_root=inverse_root, scale=scale,
+                                   stream=self._stream())
+        return t
+
+
+class FourStepNTT768:
+    def __init__(self, backend, logn, omega, group=None, modulus=F.FR, directions=("forward", "inverse")):
+        self.be = backend
+        self.group = group
+        self.G = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.logn = logn
+        self.log_n1 = logn // 2
+        self.log_n2 = logn - self.log_n1
+        self.n1, self.n2, self.n = 1 << self.log_n1, 1 << self.log_n2, 1 << logn
+        assert self.n1 % self.G == 0 and self.n2 % self.G == 0, "both sides of the matrix must split across the ranks"
+        self.C, self.R = self.n2 // self.G, self.n1 // self.G
+        self.omega = np.ascontiguousarray(omega, dtype=np.uint32)
+        self.w_col = F.mont_pow(self.omega, self.n2, modulus)  # n1-th root
+        self.w_row = F.mont_pow(self.omega, self.n1, modulus)  # n2-th root
+        self.tw_fwd = self.tw_inv = None
+        if "forward" in directions:   # rows (rank*R + r), all columns i2
+            self.tw_fwd = self.be.table(self.R, self.n2, self.rank * self.R, 0, self.n, self.omega)
+        if "inverse" in directions:   # all rows k1, columns rank*C + c; carries n^-1
+            self.tw_inv = self.be.table(self.n1, self.C, 0, self.rank * self.C, self.n, self.omega, inverse_root=True, scale=True)
+
+    # shapes of the two layouts on this rank
+    def column_block_shape(self):
+        return (self.n1, self.C, F.NL)
+
+    def row_block_shape(self):
+        return (self.R, self.n2, F.NL)
+
+    def _all_to_all(self, send):
+        if self.G == 1:
+            return send
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=self.group)
+        return recv
+
+    def forward(self, x):
+        """x: column-block (n1, C, 24) int32, overwritten.  Returns row-block (R, n2, 24)."""
+        assert tuple(x.shape) == self.column_block_shape()
+        self.be.ntt(x, self.n1, 1, _ilog2(self.C), self.w_col)
+        recv = self._all_to_all(x.view(self.G, self.R, self.C, F.NL))        # [g, r, c]: rows of this rank from every g
+        y = recv.permute(1, 0, 2, 3).contiguous().view(self.R, self.n2, F.NL)  # [r, i2 = g*C + c]
+        self.be.ntt(y, self.n2, self.R, 0, self.w_row, pre_table=self.tw_fwd)
+        return y
+
+    def inverse(self, y):
+        """y: row-block (R, n2, 24) int32, overwritten.  Returns column-block (n1, C, 24)."""
+        assert tuple(y.shape) == self.row_block_shape()
+        self.be.ntt(y, self.n2, self.R, 0, self.w_row, inverse_root=True, no_scale=True)
+        send = y.view(self.R, self.G, self.C, F.NL).permute(1, 0, 2, 3).contiguous()  # [g, r, c]
+        x = self._all_to_all(send).view(self.n1, self.C, F.NL)                         # [k1 = h*R + r, c]
+        self.be.ntt(x, self.n1, 1, _ilog2(self.C), self.w_col, inverse_root=True, no_scale=True, pre_table=self.tw_inv)
+        return x
+
+
+# ---- helpers to move between a natural-order vector and the two layouts (tests, examples)
+def to_column_block(a, logn, G, rank):
+    """a: (n, 24) natural order -> this rank's (n1, C, 24) column block"""
+    n1, n2 = 1 << (logn // 2), 1 << (logn - logn // 2)
+    C = n2 // G
+    return a.reshape(n1, n2, F.NL)[:, rank * C:(rank + 1) * C].clone() if torch.is_tensor(a) else \
+        np.ascontiguousarray(a.reshape(n1, n2, F.NL)[:, rank * C:(rank + 1) * C])
+
+
+def from_row_blocks(blocks, logn):
+    """list over ranks of (R, n2, 24) row blocks -> (n, 24) natural order: A[k1 + n1*k2] = y[k1][k2]"""
+    n1, n2 = 1 << (logn // 2), 1 << (logn - logn // 2)
+    y = np.concatenate([np.asarray(b) for b in blocks], axis=0)  # (n1, n2, 24) indexed [k1][k2]
+    return np.ascontiguousarray(y.transpose(1, 0, 2)).reshape(n1 * n2, F.NL)

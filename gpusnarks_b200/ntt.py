@@ -15,6 +15,7 @@ from . import _lib
 FIELD_FR = 0
 FIELD_FQ = 1
 NL = 24
+FLAG_INVERSE_ROOT, FLAG_NO_SCALE, FLAG_SCALE_TABLE = 1, 2, 4
 
 ERRORS = {1: "INVALID_ARG", 2: "NOT_POW2", 3: "TOO_LARGE", 4: "BAD_OMEGA", 5: "CUDA", 6: "NO_DEVICE", 7: "BAD_MODULUS"}
 
@@ -108,6 +109,18 @@ class Context:
         omega = _limbs(omega)
         self._check(self.L.gsn_ntt768_strided_device(self._h, C.c_void_p(dptr), int(n), int(batch), int(log_r), _ptr(omega),
                                                      int(bool(inverse)), C.c_void_p(stream or 0)))
+
+    def ntt768_device_ex(self, dptr, n, omega, batch=1, log_r=0, inverse_root=False, no_scale=False, pre_table=None, stream=None):
+        omega = _limbs(omega)
+        flags = (FLAG_INVERSE_ROOT if inverse_root else 0) | (FLAG_NO_SCALE if no_scale else 0)
+        self._check(self.L.gsn_ntt768_device_ex(self._h, C.c_void_p(dptr), int(n), int(batch), int(log_r), _ptr(omega), flags,
+                                                C.c_void_p(pre_table or 0), C.c_void_p(stream or 0)))
+
+    def fourstep_table768(self, dptr, rows, cols, row0, col0, n_total, omega, inverse_root=False, scale=False, stream=None):
+        omega = _limbs(omega)
+        flags = (FLAG_INVERSE_ROOT if inverse_root else 0) | (FLAG_SCALE_TABLE if scale else 0)
+        self._check(self.L.gsn_fourstep_table768(self._h, C.c_void_p(dptr), int(rows), int(cols), int(row0), int(col0), int(n_total),
+                                                 _ptr(omega), flags, C.c_void_p(stream or 0)))
 
     def prepare768(self, n, omega, inverse=False, batch=1):
         omega = _limbs(omega)

@@ -79,14 +79,25 @@ int gsn_ntt768_device(gsn_ctx *ctx, uint32_t *d_limbs, size_t n, size_t batch, c
 int gsn_ntt768_prepare(gsn_ctx *ctx, size_t n, size_t batch, const uint32_t omega[GSN_FP768_LIMBS], int inverse);
 
 /* Partial transform used by the multi-GPU four-step driver: `d_limbs` holds
- * batch x n x 2^log_r elements indexed (batch | i | r); transforms along i only.
- * pre_scale (device pointer, 24 limbs, may be NULL) multiplies every input element. */
+ * batch x n x 2^log_r elements indexed (batch | i | r); transforms along i only. */
 int gsn_ntt768_strided_device(gsn_ctx *ctx, uint32_t *d_limbs, size_t n, size_t batch, unsigned log_r,
                               const uint32_t omega[GSN_FP768_LIMBS], int inverse, void *stream);
-/* d_limbs[i] *= omega^((row0 + i / cols) * (col0 + i % cols)) * (scale ? *scale : 1),
- * i < rows*cols: the four-step twiddle between the column and the row transforms. */
-int gsn_fp768_twiddle_device(gsn_ctx *ctx, uint32_t *d_limbs, size_t rows, size_t cols, size_t row0, size_t col0,
-                             size_t n_total, const uint32_t omega[GSN_FP768_LIMBS], void *stream);
+/* General form.  flags: GSN_FLAG_INVERSE_ROOT uses omega^-1 and (unless GSN_FLAG_NO_SCALE)
+ * scales by n^-1.  d_pre_table (device, batch*n*2^log_r elements, may be NULL): every input
+ * element is first multiplied by the table entry of the same index -- the four-step twiddles
+ * produced by gsn_fourstep_table768, fused into the first pass of the transform. */
+#define GSN_FLAG_INVERSE_ROOT 1u
+#define GSN_FLAG_NO_SCALE 2u
+#define GSN_FLAG_SCALE_TABLE 4u
+int gsn_ntt768_device_ex(gsn_ctx *ctx, uint32_t *d_limbs, size_t n, size_t batch, unsigned log_r,
+                         const uint32_t omega[GSN_FP768_LIMBS], unsigned flags, const uint32_t *d_pre_table, void *stream);
+/* d_table[r * cols + c] = omega^(+-(row0 + r) * (col0 + c))  [* n_total^-1 with GSN_FLAG_SCALE_TABLE],
+ * r < rows, c < cols, omega a primitive n_total-th root (GSN_FLAG_INVERSE_ROOT: omega^-1):
+ * the twiddles between the column and the row transforms of a four-step (Bailey) NTT for
+ * the shard that owns rows row0.. and columns col0.. (reference structure: the omega_j /
+ * omega_step factors of _basic_parallel_radix2_FFT_inner, test/fft_host.h:79-101). */
+int gsn_fourstep_table768(gsn_ctx *ctx, uint32_t *d_table, size_t rows, size_t cols, size_t row0, size_t col0, size_t n_total,
+                          const uint32_t omega[GSN_FP768_LIMBS], unsigned flags, void *stream);
 
 /* ---- field arithmetic on arrays (parity tests of the device Montgomery code against the
  * oracle; reference device_field_operators.h:190-214).  op: 0 mul (a*b*R^-1), 1 add, 2 sub. */

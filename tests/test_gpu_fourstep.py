@@ -1,0 +1,45 @@
+"""Four-step driver on the GPU: single rank (no exchange) in-process, and -- when the box has
+at least two GPUs -- two ranks under torchrun with the NCCL all-to-all."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import fieldgen
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("logn", [4, 9, 12, 16])
+def test_single_rank_fourstep_vs_oracle(ctx, logn):
+    import torch
+    from gpusnarks_b200 import fourstep
+    dev = torch.device("cuda", 0)
+    n = 1 << logn
+    a = fieldgen.random_elements(n, 77 + logn)
+    w = fieldgen.omega768(n)
+    plan = fourstep.FourStepNTT768(fourstep.CudaBackend(ctx, dev), logn, w)
+    x = torch.from_numpy(fourstep.to_column_block(a, logn, 1, 0).view(np.int32)).to(dev)
+    x0 = x.clone()
+    y = plan.forward(x)
+    torch.cuda.synchronize()
+    got = fourstep.from_row_blocks([y.cpu().numpy().view(np.uint32)], logn)
+    assert (got == O.fft768(a, w, 3 if n >= 64 else -1)).all()
+    back = plan.inverse(y)
+    torch.cuda.synchronize()
+    assert bool((back == x0).all())
+
+
+def test_two_rank_fourstep_nccl():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29731", os.path.join(ROOT, "tests", "run_fourstep_multi.py"), "14", "20"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "FOURSTEP_OK" in out.stdout
