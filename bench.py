@@ -13,7 +13,7 @@ A "step" is one whole transform of synthetic random field elements.
   e2e     the same transform through the host-pointer C ABI call (gsn_ntt768_host): pinned
           host buffer -> H2D -> transform -> D2H inside the timed region, every step.
   roofline  the dominant kernel (ntt768_pass) against the INT32 multiply issue peak measured
-          in this same process (gsn_int32_issue_rates, plain IMAD.WIDE.U32), algorithmic work
+          in this same process (gsn_int32_issue_rates, IMAD.WIDE.U32 accumulate form), algorithmic work
           = 1176 wide MACs per butterfly; HBM figures given alongside.
   cpu_baseline  the reference's own host FFT (oracle/_ref/libref_verbatim.so, compiled from
           /root/reference, test/fft_host.h via the host half of test/main.cpp:64-76) timed on
@@ -311,7 +311,7 @@ def main():
             "achieved": achieved / 1e12, "peak": p_mac / 1e12, "unit": "T wide-MAC/s (32x32+64 IMAD.WIDE.U32)",
             "frac": achieved / p_mac,
             "algorithmic_macs_per_butterfly": MACS_PER_BUTTERFLY,
-            "peak_source": "gsn_int32_issue_rates (plain IMAD.WIDE.U32, no carry chain) measured in this process",
+            "peak_source": "gsn_int32_issue_rates mode 2: IMAD.WIDE.U32 accumulate form, 8 independent accumulators, distinct multiplicands, measured in this process (SASS-verified loop)",
             "int32_issue_rates_per_s": rates["rates"],
             "launches_per_step": kernels_per_step,
             "avg_launch_ms": (ms_step / kernels_per_step) if kernels_per_step else None,

@@ -145,16 +145,15 @@ int gsn_ntt32_host(gsn_ctx *ctx, uint32_t *a, size_t n, uint32_t omega, uint32_t
     if (!ctx || !a) return fail(GSN_ERR_INVALID_ARG, "null argument");
     int rc = check_n(n, 1);
     if (rc) return rc;
-    DevBuf d;
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
         CU(cudaSetDevice(ctx->device));
-        if ((rc = dev_alloc(d, n * 4))) return rc;
-        CU(cudaMemcpyAsync(d.p, a, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if ((rc = ensure_io(ctx, n * 4))) return rc;
+        CU(cudaMemcpyAsync(ctx->io.p, a, n * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
-    if ((rc = gsn_ntt32_device(ctx, (uint32_t *)d.p, n, 1, omega, mod, inverse, nullptr))) return rc;
+    if ((rc = gsn_ntt32_device(ctx, (uint32_t *)ctx->io.p, n, 1, omega, mod, inverse, nullptr))) return rc;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    CU(cudaMemcpyAsync(a, d.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(a, ctx->io.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return GSN_OK;
 }

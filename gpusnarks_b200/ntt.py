@@ -164,9 +164,7 @@ class Context:
         rates = (C.c_double * 16)()
         nm, sm, khz = C.c_int(), C.c_int(), C.c_int()
         self._check(self.L.gsn_int32_issue_rates(self._h, rates, 16, C.byref(nm), C.byref(sm), C.byref(khz)))
-        names = ["imad_lo", "imad_hi_invariant", "imad_wide", "imad_wide_x_short_chain", "imad_wide_with_iadd3", "imad_hi",
-                 "imad_lo_carry_chain", "imad_hi_carry_chain", "iadd3_x_chain", "imad_wide_x_long_chain", "imad_lo_hi_pairs",
-                 "imad_wide_variant"]
+        names = ["imad_lo", "imad_hi", "imad_wide", "imad_wide_shared_operands", "imad_wide_x_chain", "iadd3_x_chain"]
         return {"rates": {names[k]: rates[k] for k in range(nm.value)}, "sm_count": sm.value, "sm_clock_khz": khz.value}
 
 

@@ -120,13 +120,11 @@ int gsn_memcpy_d2h(gsn_ctx *ctx, void *hptr, const void *dptr, size_t bytes);
 int gsn_ctx_synchronize(gsn_ctx *ctx);
 
 /* ---- measurement: INT32 multiply issue rates of the device (roofline denominator for the
- * 768-bit path).  rates[k] = instructions of kind k per second, chip wide, thread-level:
- *  0 IMAD (mad.lo)            1 mad.hi with loop-invariant operands (hoistable; ignore)
- *  2 IMAD.WIDE.U32 (mad.wide, no carry)  <- the "wide MAC" peak used as roofline denominator
- *  3 IMAD.WIDE.U32.X short carry chains  4 IMAD.WIDE.U32 interleaved 1:1 with IADD3 (rate of the wide MACs)
- *  5 IMAD.HI.U32              6 IMAD lo with carry chains     7 IMAD.HI with carry chains
- *  8 IADD3.X carry chains     9 IMAD.WIDE.U32.X one long chain
- * 10 mad.lo + mad.hi pairs (rate of single instructions)     11 IMAD.WIDE.U32 loop-variant operand
+ * 768-bit path).  rates[k] = thread-level instructions of kind k per second, chip wide, from
+ * loops with 8 independent accumulators and distinct multiplicand registers:
+ *  0 IMAD (mad.lo)   1 IMAD.HI (mad.hi)   2 IMAD.WIDE.U32 accumulate form (32x32+64 -> 64): the
+ *  "wide MAC" peak used as roofline denominator   3 IMAD.WIDE.U32 with shared multiplicands
+ *  4 IMAD.WIDE.U32.X carry chains (the form the CIOS product issues)   5 IADD3.X carry chains.
  * At most max_modes entries are written; *n_modes receives the count. */
 int gsn_int32_issue_rates(gsn_ctx *ctx, double *rates, int max_modes, int *n_modes, int *sm_count, int *sm_clock_khz);
 /* time `reps` back-to-back device transforms with CUDA events on the context's stream;
