@@ -58,13 +58,15 @@ class CudaBackend:
 
 
 class FourStepNTT768:
-    def __init__(self, backend, logn, omega, group=None, modulus=F.FR, directions=("forward", "inverse")):
+    def __init__(self, backend, logn, omega, group=None, modulus=F.FR, directions=("forward", "inverse"), log_n1=None):
         self.be = backend
         self.group = group
         self.G = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.logn = logn
-        self.log_n1 = logn // 2
+        # the short side is one shared-memory pass (<= 2^10) when the transform is large enough:
+        # 2^24 = 2^10 x 2^14 is three passes in all, 2^12 x 2^12 would be four
+        self.log_n1 = split_log_n1(logn) if log_n1 is None else log_n1
         self.log_n2 = logn - self.log_n1
         self.n1, self.n2, self.n = 1 << self.log_n1, 1 << self.log_n2, 1 << logn
         assert self.n1 % self.G == 0 and self.n2 % self.G == 0, "both sides of the matrix must split across the ranks"
@@ -111,17 +113,23 @@ class FourStepNTT768:
         return x
 
 
+def split_log_n1(logn):
+    return min(10, logn // 2)
+
+
 # ---- helpers to move between a natural-order vector and the two layouts (tests, examples)
-def to_column_block(a, logn, G, rank):
+def to_column_block(a, logn, G, rank, log_n1=None):
     """a: (n, 24) natural order -> this rank's (n1, C, 24) column block"""
-    n1, n2 = 1 << (logn // 2), 1 << (logn - logn // 2)
+    log_n1 = split_log_n1(logn) if log_n1 is None else log_n1
+    n1, n2 = 1 << log_n1, 1 << (logn - log_n1)
     C = n2 // G
     return a.reshape(n1, n2, F.NL)[:, rank * C:(rank + 1) * C].clone() if torch.is_tensor(a) else \
         np.ascontiguousarray(a.reshape(n1, n2, F.NL)[:, rank * C:(rank + 1) * C])
 
 
-def from_row_blocks(blocks, logn):
+def from_row_blocks(blocks, logn, log_n1=None):
     """list over ranks of (R, n2, 24) row blocks -> (n, 24) natural order: A[k1 + n1*k2] = y[k1][k2]"""
-    n1, n2 = 1 << (logn // 2), 1 << (logn - logn // 2)
+    log_n1 = split_log_n1(logn) if log_n1 is None else log_n1
+    n1, n2 = 1 << log_n1, 1 << (logn - log_n1)
     y = np.concatenate([np.asarray(b) for b in blocks], axis=0)  # (n1, n2, 24) indexed [k1][k2]
     return np.ascontiguousarray(y.transpose(1, 0, 2)).reshape(n1 * n2, F.NL)

@@ -1,0 +1,66 @@
+"""CPU: the committed golden fixtures are reproduced by the oracle; the executable model of the
+kernel index math (tools/model_passes.py) agrees with the DFT; host-side helpers of the product
+(gpusnarks_b200/field.py, planner constants) agree with tests/pyref.py."""
+import hashlib
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import fieldgen
+import oracle_lib as O
+import pyref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def test_golden_ntt768_reproduced_by_oracle():
+    with open(os.path.join(GOLDEN, "ntt768.json")) as f:
+        gold = json.load(f)
+    for case in gold["cases"]:
+        n = 1 << case["logn"]
+        a = fieldgen.random_elements(n, case["seed"])
+        assert hashlib.sha256(a.tobytes()).hexdigest() == case["input_sha256"], "synthetic input generator drifted"
+        out = O.fft768(a, fieldgen.omega768(n), 3 if n >= 64 else (0 if case["inverse"] else -1), inverse=case["inverse"])
+        assert hashlib.sha256(out.tobytes()).hexdigest() == case["sha256"]
+        assert [int(x) for x in out[0]] == case["first"]
+
+
+def test_golden_ntt32_reproduced_by_oracle():
+    with open(os.path.join(GOLDEN, "ntt32.json")) as f:
+        gold = json.load(f)
+    for case in gold["cases"]:
+        if case["logn"] > 20:
+            continue  # the 2^22 cases take a few seconds each; covered on the GPU box
+        n = 1 << case["logn"]
+        a = fieldgen.random_u32(n, case["seed"], case["mod"])
+        assert hashlib.sha256(a.tobytes()).hexdigest() == case["input_sha256"]
+        out = O.fft32(a, fieldgen.omega32(n, case["mod"]), case["mod"], 3 if n >= 64 else (0 if case["inverse"] else -1), inverse=case["inverse"])
+        assert hashlib.sha256(out.tobytes()).hexdigest() == case["sha256"]
+
+
+def test_kernel_index_model():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "model_passes.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "model_passes: ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_product_field_helpers_match_pyref():
+    from gpusnarks_b200 import field as F
+    assert F.FR == pyref.FR and F.FQ == pyref.FQ and F.P32 == pyref.P32
+    for n in (1, 2, 1 << 10, 1 << 20, 1 << 30):
+        w = F.root_of_unity768(n)
+        assert (w == fieldgen.omega768(n)).all()
+        assert F.from_limbs(F.mont_pow(w, n)) == pyref.RMONT % pyref.FR
+    w = F.root_of_unity768(1 << 12)
+    assert (F.mont_pow(w, 1 << 6) == fieldgen.omega768(1 << 6)).all()
+    assert F.root_of_unity32(1 << 22) == fieldgen.omega32(1 << 22)
+
+
+def test_generated_constants_header_is_current():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "derive_constants.py")], capture_output=True, text=True, check=True).stdout
+    with open(os.path.join(ROOT, "include", "gsn_constants.h")) as f:
+        assert f.read() == out

@@ -1,0 +1,26 @@
+"""CPU: compile and run the C++ host-side checks (product field headers vs the oracle; the
+reference-shaped drop-in driver at least compiles and links against the C ABI)."""
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+
+
+def test_host_field_types_match_oracle(tmp_path):
+    exe = str(tmp_path / "test_host_fields")
+    subprocess.check_call([CXX, "-O2", "-fopenmp", "-std=c++17", "-Wall", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle"),
+                           "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_host_fields.cpp")])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "host fields ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_drop_in_driver_compiles_and_links(tmp_path):
+    """reference test/main.cpp shape (best_fft<fields::Scalar>(v, omega) then the host FFT) against libgpusnarks_b200.so"""
+    from gpusnarks_b200 import build
+    build.build()
+    exe = str(tmp_path / "test_fft_main")
+    subprocess.check_call([CXX, "-O2", "-fopenmp", "-std=c++17", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle"),
+                           "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_fft_main.cpp"),
+                           "-L" + os.path.join(ROOT, "gpusnarks_b200"), "-lgpusnarks_b200", "-Wl,-rpath," + os.path.join(ROOT, "gpusnarks_b200")])
+    assert os.path.exists(exe)
