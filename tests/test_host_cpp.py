@@ -24,3 +24,19 @@ def test_drop_in_driver_compiles_and_links(tmp_path):
                            "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_fft_main.cpp"),
                            "-L" + os.path.join(ROOT, "gpusnarks_b200"), "-lgpusnarks_b200", "-Wl,-rpath," + os.path.join(ROOT, "gpusnarks_b200")])
     assert os.path.exists(exe)
+
+
+def test_reference_main_cpp_compiles_unmodified(tmp_path):
+    """the reference's own test/main.cpp (-DFFT) compiles and links against this repo's headers and
+    library without edits: same header paths, same template, same field type surface"""
+    import pytest
+    ref = "/root/reference/test/main.cpp"
+    if not os.path.exists(ref):
+        pytest.skip("reference tree absent")
+    from gpusnarks_b200 import build
+    build.build()
+    exe = str(tmp_path / "ref_main")
+    subprocess.check_call([CXX, "-O2", "-fopenmp", "-std=c++17", "-w", "-DFFT", "-I" + os.path.join(ROOT, "include"), "-I/root/reference/test",
+                           ref, "-L" + os.path.join(ROOT, "gpusnarks_b200"), "-lgpusnarks_b200",
+                           "-Wl,-rpath," + os.path.join(ROOT, "gpusnarks_b200"), "-o", exe])
+    assert os.path.exists(exe)
