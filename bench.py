@@ -141,6 +141,15 @@ def cpu_reference_run(sample_logn, steps, warmup):
 
 
 # ------------------------------------------------------------------------------ main
+def emit(line):
+    """the ONE JSON line goes to the real stdout; everything else this process (or NCCL) prints goes to stderr"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)  # libraries (e.g. NCCL's version banner) write to fd 1: keep the bench output a single line
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -171,7 +180,7 @@ def main():
                 "scaling": "strong" if N > 1 else "weak", "vs_baseline": None, "dtype": "u32x24 (768-bit Montgomery, integer)",
                 "data": "synthetic", "config": config, "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "butterflies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -335,7 +344,7 @@ def main():
                 line["cpu_baseline"] = cpu_reference_run(min(args.cpu_sample_log_n, logn), 1, 0)
             except Exception as e:  # the bench line must still print
                 line["cpu_baseline"] = {"error": str(e)}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

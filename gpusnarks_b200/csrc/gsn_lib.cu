@@ -23,6 +23,7 @@
 #include "../../include/fields/fp768_host.h"
 #include "microbench.cuh"
 #include "ntt32.cuh"
+#include "ntt32_fast.cuh"
 #include "ntt768.cuh"
 
 namespace {
@@ -78,6 +79,13 @@ struct Plan32 {
     DevBuf wloc;                  // pairs (w, w') Shoup form
     std::vector<std::unique_ptr<DevBuf>> pre;
     std::vector<uint64_t> pre_mask;
+    // fast path (two passes, digits of 9..12 stages): in-tile four-step tables per pass and the
+    // two-level power tables for the inter-pass twiddle
+    bool fast = false;
+    std::vector<std::unique_ptr<DevBuf>> tA, tB;
+    DevBuf t_lo, t_hi, tG;
+    uint32_t lo_bits = 0;
+    gsn::Ntt32Consts consts;
 };
 
 std::vector<uint32_t> plan_digits(uint32_t logn, uint32_t max_log) {

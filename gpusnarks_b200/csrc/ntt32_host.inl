@@ -2,7 +2,7 @@
 // Replaces best_fft for the reference's 32-bit field sketch (fields/dummy_field.h:24-62).
 namespace {
 
-constexpr int MAX_PASS_LOG32 = 11;   // stages per pass (2^22 = 11 + 11)
+constexpr int MAX_PASS_LOG32 = 12;   // stages per pass (2^22 = 11 + 11, 2^24 = 12 + 12)
 constexpr int MAX_TILE_LOG32 = 13;   // elements per CTA tile (32 KiB of shared memory)
 constexpr int NTT32_THREADS = 512;
 
@@ -52,24 +52,76 @@ int get_plan32(gsn_ctx *ctx, uint32_t logn, uint32_t omega, uint32_t mod, int in
     if ((rc = dev_alloc(pl->wloc, half * 8))) return rc;
     gsn::pow_table32<<<(unsigned)((half + 255) / 256), 256, 0, st>>>((uint2 *)pl->wloc.p, w_eff, half, pl->lmax ? (n >> pl->lmax) : 0, 1, mod);
     ctx->launches++;
-    DevBuf t_lo, t_hi;
+    pl->fast = P == 2 && pl->digits[0] >= 9 && pl->digits[0] <= 12 && pl->digits[1] >= 9 && pl->digits[1] <= 12;
     if (P > 1) {
         const uint32_t lo_bits = std::min<uint32_t>(11, logn);
+        pl->lo_bits = lo_bits;
+        DevBuf &t_lo = pl->t_lo, &t_hi = pl->t_hi;
         if ((rc = dev_alloc(t_lo, (1ull << lo_bits) * 8)) || (rc = dev_alloc(t_hi, (n >> lo_bits) * 8))) return rc;
         gsn::pow_table32<<<(unsigned)((n >> lo_bits) + 255) / 256, 256, 0, st>>>((uint2 *)t_hi.p, w_eff, n >> lo_bits, 1ull << lo_bits, 1, mod);
         ctx->launches++;
-        for (size_t q = P - 1; q >= 1; --q) {
-            uint32_t logN = 0;
-            for (size_t i = q - 1; i < P; ++i) logN += pl->digits[i];
-            // the low table carries n^-1 for boundary 1 of an inverse plan
-            gsn::pow_table32<<<(unsigned)(((1ull << lo_bits) + 255) / 256), 256, 0, st>>>((uint2 *)t_lo.p, w_eff, 1ull << lo_bits, 1, q == 1 ? n_inv : 1, mod);
-            pl->pre[q] = std::make_unique<DevBuf>();
-            if ((rc = dev_alloc(*pl->pre[q], (1ull << logN) * 8))) return rc;
-            pl->pre_mask[q] = (1ull << logN) - 1;
-            const uint64_t cnt = 1ull << logN;
-            gsn::build_pretw32<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>((uint2 *)pl->pre[q]->p, (const uint2 *)t_lo.p, (const uint2 *)t_hi.p, logN,
-                                                                               logN - pl->digits[q - 1], logn - logN, lo_bits, mod);
+        if (pl->fast) {
+            // in-tile four-step tables (unscaled low table), then the low table is rebuilt carrying n^-1
+            gsn::pow_table32<<<(unsigned)(((1ull << lo_bits) + 255) / 256), 256, 0, st>>>((uint2 *)t_lo.p, w_eff, 1ull << lo_bits, 1, 1, mod);
+            ctx->launches++;
+            pl->tA.resize(P);
+            pl->tB.resize(P);
+            for (size_t q = 0; q < P; ++q) {
+                const uint32_t L = pl->digits[q];
+                const uint32_t a = L >= 10 ? 4 : 3, c = L == 12 ? 4 : 3, b = L - a - c;
+                pl->tA[q] = std::make_unique<DevBuf>();
+                pl->tB[q] = std::make_unique<DevBuf>();
+                if ((rc = dev_alloc(*pl->tA[q], (1ull << L) * 8)) || (rc = dev_alloc(*pl->tB[q], (1ull << (b + c)) * 8))) return rc;
+                gsn::build_pretw32<<<(unsigned)(((1ull << L) + 255) / 256), 256, 0, st>>>((uint2 *)pl->tA[q]->p, (const uint2 *)t_lo.p, (const uint2 *)t_hi.p, L,
+                                                                                         b + c, logn - L, lo_bits, mod);
+                gsn::build_pretw32<<<(unsigned)(((1ull << (b + c)) + 255) / 256), 256, 0, st>>>((uint2 *)pl->tB[q]->p, (const uint2 *)t_lo.p, (const uint2 *)t_hi.p,
+                                                                                               b + c, c, logn - (b + c), lo_bits, mod);
+                ctx->launches += 2;
+            }
+            // low table of the inter-pass twiddle: w^e * n^-1 (inverse plans) * 2^32, i.e. Montgomery form
+            const uint32_t r32 = (uint32_t)((1ull << 32) % mod);
+            gsn::pow_table32<<<(unsigned)(((1ull << lo_bits) + 255) / 256), 256, 0, st>>>((uint2 *)t_lo.p, w_eff, 1ull << lo_bits, 1, mulmod_h(n_inv, r32, mod), mod);
+            // per-row step of the recurrence in pass 2: tG[k] = w^(k * QA), QA = 2^(B+C) of the second digit
+            {
+                const uint32_t L2 = pl->digits[1];
+                const uint32_t a2 = L2 >= 10 ? 4 : 3;
+                const uint64_t rows = 1ull << pl->digits[0];
+                if ((rc = dev_alloc(pl->tG, rows * 8))) return rc;
+                gsn::pow_table32<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>((uint2 *)pl->tG.p, powmod_h(w_eff, 1ull << (L2 - a2), mod), rows, 1, 1, mod);
+            }
             ctx->launches += 2;
+            pl->pre_mask[1] = n - 1;
+            gsn::Ntt32Consts &k = pl->consts;
+            memset(&k, 0, sizeof(k));
+            const uint32_t w16 = powmod_h(w_eff, n >> 4, mod);
+            uint32_t acc = 1;
+            for (int e = 0; e < 8; ++e) {
+                k.rt[e] = make_uint2(acc, (uint32_t)(((uint64_t)acc << 32) / mod));
+                acc = mulmod_h(acc, w16, mod);
+            }
+            k.p = mod;
+            {
+                uint32_t inv = 1;  // Newton: p^-1 mod 2^32
+                for (int i = 0; i < 5; ++i) inv *= 2 - mod * inv;
+                k.pinv = inv;
+            }
+            k.pre_k_bits = pl->digits[0];
+            k.pre_logn = logn;
+            k.pre_lo_bits = lo_bits;
+        } else {
+            for (size_t q = P - 1; q >= 1; --q) {
+                uint32_t logN = 0;
+                for (size_t i = q - 1; i < P; ++i) logN += pl->digits[i];
+                // the low table carries n^-1 for boundary 1 of an inverse plan
+                gsn::pow_table32<<<(unsigned)(((1ull << lo_bits) + 255) / 256), 256, 0, st>>>((uint2 *)t_lo.p, w_eff, 1ull << lo_bits, 1, q == 1 ? n_inv : 1, mod);
+                pl->pre[q] = std::make_unique<DevBuf>();
+                if ((rc = dev_alloc(*pl->pre[q], (1ull << logN) * 8))) return rc;
+                pl->pre_mask[q] = (1ull << logN) - 1;
+                const uint64_t cnt = 1ull << logN;
+                gsn::build_pretw32<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>((uint2 *)pl->pre[q]->p, (const uint2 *)t_lo.p, (const uint2 *)t_hi.p, logN,
+                                                                                   logN - pl->digits[q - 1], logn - logN, lo_bits, mod);
+                ctx->launches += 2;
+            }
         }
     } else if (inverse) {
         pl->pre[0] = std::make_unique<DevBuf>();
@@ -84,7 +136,63 @@ int get_plan32(gsn_ctx *ctx, uint32_t logn, uint32_t omega, uint32_t mod, int in
     return GSN_OK;
 }
 
+template <int A, int B, int C, bool SLOT_FAST, bool PRE>
+int launch_fast32(gsn_ctx *ctx, unsigned grid, cudaStream_t st, const uint32_t *src, uint32_t *dst, const uint2 *tA, const uint2 *tB,
+                  const uint2 *t_lo, const uint2 *t_hi, const uint2 *tG, const gsn::PassGeom &g, const gsn::Ntt32Consts &k) {
+    constexpr int MINB = (A + B + C) == 12 ? 1 : 2;
+    auto kern = gsn::ntt32_fast_pass<A, B, C, SLOT_FAST, PRE, MINB>;
+    static bool attr_done = false;  // per instantiation; one device per process in this library's deployment model
+    if (!attr_done) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsn::FastTile<A, B, C>::SMEM_BYTES));
+        attr_done = true;
+    }
+    kern<<<grid, 512, gsn::FastTile<A, B, C>::SMEM_BYTES, st>>>(src, dst, tA, tB, t_lo, t_hi, tG, g, k);
+    ctx->launches++;
+    return GSN_OK;
+}
+
+template <bool SLOT_FAST, bool PRE>
+int dispatch_fast32(uint32_t L, gsn_ctx *ctx, unsigned grid, cudaStream_t st, const uint32_t *src, uint32_t *dst, const uint2 *tA,
+                    const uint2 *tB, const uint2 *t_lo, const uint2 *t_hi, const uint2 *tG, const gsn::PassGeom &g, const gsn::Ntt32Consts &k) {
+    switch (L) {
+        case 9: return launch_fast32<3, 3, 3, SLOT_FAST, PRE>(ctx, grid, st, src, dst, tA, tB, t_lo, t_hi, tG, g, k);
+        case 10: return launch_fast32<4, 3, 3, SLOT_FAST, PRE>(ctx, grid, st, src, dst, tA, tB, t_lo, t_hi, tG, g, k);
+        case 11: return launch_fast32<4, 4, 3, SLOT_FAST, PRE>(ctx, grid, st, src, dst, tA, tB, t_lo, t_hi, tG, g, k);
+        default: return launch_fast32<4, 4, 4, SLOT_FAST, PRE>(ctx, grid, st, src, dst, tA, tB, t_lo, t_hi, tG, g, k);
+    }
+}
+
+int launch_ntt32_fast(gsn_ctx *ctx, Plan32 *pl, uint32_t *d_data, size_t batch, cudaStream_t st) {
+    const uint64_t total = (uint64_t)batch << pl->logn;
+    int rc;
+    if ((rc = ensure_work(ctx, total * 4))) return rc;
+    uint32_t *work = (uint32_t *)ctx->work.p;
+    for (size_t q = 0; q < 2; ++q) {
+        gsn::PassGeom g;
+        memset(&g, 0, sizeof(g));
+        g.log_l = pl->digits[q];
+        g.log_s = q == 0 ? pl->digits[1] : 0;
+        g.final_natural = q == 1;
+        g.canonical = 1;
+        g.ndig = 2;
+        g.dig[0] = pl->digits[0];
+        g.dig[1] = pl->digits[1];
+        g.logn = pl->logn;
+        g.has_pre = q == 1;
+        g.pre_mask = pl->pre_mask[q];
+        const unsigned grid = (unsigned)((total >> g.log_l) / 8);
+        const uint2 *tA = (const uint2 *)pl->tA[q]->p, *tB = (const uint2 *)pl->tB[q]->p;
+        const uint2 *t_lo = (const uint2 *)pl->t_lo.p, *t_hi = (const uint2 *)pl->t_hi.p, *tG = (const uint2 *)pl->tG.p;
+        if (q == 0) rc = dispatch_fast32<true, false>(g.log_l, ctx, grid, st, d_data, work, tA, tB, t_lo, t_hi, tG, g, pl->consts);
+        else rc = dispatch_fast32<false, true>(g.log_l, ctx, grid, st, work, d_data, tA, tB, t_lo, t_hi, tG, g, pl->consts);
+        if (rc) return rc;
+    }
+    CU(cudaGetLastError());
+    return GSN_OK;
+}
+
 int launch_ntt32(gsn_ctx *ctx, Plan32 *pl, uint32_t *d_data, size_t batch, cudaStream_t st) {
+    if (pl->fast) return launch_ntt32_fast(ctx, pl, d_data, batch, st);
     const size_t P = pl->digits.size();
     const uint64_t total = (uint64_t)batch << pl->logn;
     uint32_t v2 = 0;
