@@ -140,6 +140,29 @@ def cpu_reference_run(sample_logn, steps, warmup):
             "seconds_per_step": sec}
 
 
+def bench_ntt32(ctx, hbm_peak_gbs, logn=22, batch=16, reps=12):
+    """BASELINE.json configs[1]: 32-bit prime-field NTT 2^22 on one B200 (HBM-bound).  `batch` distinct
+    16 MiB buffers (256 MiB > L2) are transformed per launch pair so that inputs come from HBM; the
+    roofline uses the algorithmic bytes of SURVEY.md section 8d: passes x 2 x n x 4 B (two passes)."""
+    from gpusnarks_b200 import field as F
+    n = 1 << logn
+    rng = np.random.Generator(np.random.PCG64(3))
+    a = rng.integers(0, F.P32, size=n * batch, dtype=np.uint64).astype(np.uint32)
+    w = F.root_of_unity32(n)
+    d = ctx.device_alloc(a.nbytes)
+    try:
+        ctx.h2d(d, a)
+        ms = ctx.time_ntt32(d, n, w, F.P32, batch=batch, reps=reps)
+    finally:
+        ctx.device_free(d)
+    t = float(np.median(ms[2:])) / batch * 1e-3
+    alg = 2 * 2 * n * 4
+    return {"workload": f"32-bit prime-field forward NTT n=2^{logn}, p=2013265921, {batch} distinct buffers per launch pair, 1xB200",
+            "us_per_transform": t * 1e6, "value": butterflies(logn) / t, "unit": "butterflies/s",
+            "roofline": {"kernel": "gsn::ntt32_fast_pass<4,4,3,...>", "bound": "hbm", "achieved": alg / t / 1e9, "peak": hbm_peak_gbs, "unit": "GB/s",
+                         "frac": alg / t / 1e9 / hbm_peak_gbs, "algorithmic_bytes_per_transform": alg, "traffic": None}}
+
+
 # ------------------------------------------------------------------------------ main
 def emit(line):
     """the ONE JSON line goes to the real stdout; everything else this process (or NCCL) prints goes to stderr"""
@@ -340,6 +363,10 @@ def main():
             "roofline": roofline,
         }
         if N == 1:
+            try:
+                line["secondary"] = {"ntt32_cfg2": bench_ntt32(ctx, hbm_peak)}
+            except Exception as e:
+                line["secondary"] = {"error": str(e)}
             try:
                 line["cpu_baseline"] = cpu_reference_run(min(args.cpu_sample_log_n, logn), 1, 0)
             except Exception as e:  # the bench line must still print
