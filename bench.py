@@ -176,7 +176,7 @@ os.dup2(2, 1)  # libraries (e.g. NCCL's version banner) write to fd 1: keep the 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", type=int, default=0, help="override the transform size (default 20 at N=1, 24 at N>1)")
@@ -262,11 +262,11 @@ def main():
         kernels_per_step = None
 
     sampler = ClockSampler(local_rank)
+    sampler.start()  # nvidia-smi takes ~0.1 s to start: begin before the warm-up so it is live for the timed region
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
     launches1 = ctx.launch_count()
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):

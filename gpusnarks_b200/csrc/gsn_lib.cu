@@ -117,6 +117,8 @@ struct gsn_ctx {
     uint64_t launches = 0;
     int sm_count = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the pipelined host-pointer path
+    cudaEvent_t ev_chunk[2][16] = {{nullptr}};
     bool attr768_set = false, attr32_set = false;
 };
 
@@ -260,7 +262,9 @@ int get_plan768(gsn_ctx *ctx, uint32_t logn, const uint32_t *omega, int inverse,
     return GSN_OK;
 }
 
-int launch_ntt768(gsn_ctx *ctx, Plan768 *pl, uint32_t *d_data, size_t batch, uint32_t log_r, const uint32_t *ext_pre, cudaStream_t st) {
+// Launches passes [q_begin, q_end) of the plan; tile range [tile0, tile0 + ntiles) of each (ntiles == 0: all).
+int launch_ntt768_range(gsn_ctx *ctx, Plan768 *pl, uint32_t *d_data, size_t batch, uint32_t log_r, const uint32_t *ext_pre, cudaStream_t st,
+                        size_t q_begin, size_t q_end, uint64_t tile0, uint64_t ntiles) {
     const size_t P = pl->digits.size();
     const uint64_t total = (uint64_t)batch << (pl->logn + log_r);
     uint32_t v2 = 0;
@@ -280,12 +284,14 @@ int launch_ntt768(gsn_ctx *ctx, Plan768 *pl, uint32_t *d_data, size_t batch, uin
     for (size_t i = 0; i < P; ++i) below += pl->digits[i];
     for (size_t q = 0; q < P; ++q) {
         below -= pl->digits[q];
+        if (q < q_begin || q >= q_end) continue;
         gsn::PassGeom g;
         memset(&g, 0, sizeof(g));
         g.log_l = pl->digits[q];
         g.log_s = below;
         g.log_r = log_r;
         g.pre_shift = log_r;
+        g.tile0 = (uint32_t)tile0;
         g.log_tile = log_tile;
         g.wloc_shift = pl->lmax - pl->digits[q];
         g.final_natural = q + 1 == P;
@@ -307,11 +313,15 @@ int launch_ntt768(gsn_ctx *ctx, Plan768 *pl, uint32_t *d_data, size_t batch, uin
         const uint32_t *src = q == 0 ? d_data : work;
         uint32_t *dst = (q + 1 == P) ? d_data : work;
         const size_t smem = ((size_t)1 << log_tile) * gsn::SMEM_PITCH4 * 16;
-        kern<<<(unsigned)(total >> log_tile), NTT768_THREADS, smem, st>>>(src, dst, (const uint32_t *)pl->wloc.p, pre, g);
+        kern<<<(unsigned)(ntiles ? ntiles : (total >> log_tile)), NTT768_THREADS, smem, st>>>(src, dst, (const uint32_t *)pl->wloc.p, pre, g);
         ctx->launches++;
     }
     CU(cudaGetLastError());
     return GSN_OK;
+}
+
+int launch_ntt768(gsn_ctx *ctx, Plan768 *pl, uint32_t *d_data, size_t batch, uint32_t log_r, const uint32_t *ext_pre, cudaStream_t st) {
+    return launch_ntt768_range(ctx, pl, d_data, batch, log_r, ext_pre, st, 0, pl->digits.size(), 0, 0);
 }
 
 int check_n(size_t n, size_t batch) {
@@ -355,6 +365,10 @@ int gsn_ctx_create(gsn_ctx **out, int device) {
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&ctx->ev0));
     CU(cudaEventCreate(&ctx->ev1));
+    CU(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    for (int d = 0; d < 2; ++d)
+        for (int i = 0; i < 16; ++i) CU(cudaEventCreateWithFlags(&ctx->ev_chunk[d][i], cudaEventDisableTiming));
     int rc = upload_field(ctx.get(), GSN_FIELD_MNT4753_FR);
     if (rc) return rc;
     *out = ctx.release();
@@ -367,6 +381,10 @@ int gsn_ctx_destroy(gsn_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     ctx->plans768.clear();
     ctx->plans32.clear();
+    for (int d = 0; d < 2; ++d)
+        for (int i = 0; i < 16; ++i) if (ctx->ev_chunk[d][i]) cudaEventDestroy(ctx->ev_chunk[d][i]);
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -441,16 +459,54 @@ int gsn_ntt768_host(gsn_ctx *ctx, uint32_t *limbs, size_t n, const uint32_t *ome
     if (!ctx || !limbs || !omega) return fail(GSN_ERR_INVALID_ARG, "null argument");
     int rc = check_n(n, 1);
     if (rc) return rc;
-    {
-        std::lock_guard<std::mutex> lk(ctx->mu);
-        CU(cudaSetDevice(ctx->device));
-        if ((rc = ensure_io(ctx, n * 96))) return rc;
-        CU(cudaMemcpyAsync(ctx->io.p, limbs, n * 96, cudaMemcpyHostToDevice, ctx->stream));
-    }
-    if ((rc = gsn_ntt768_device(ctx, (uint32_t *)ctx->io.p, n, 1, omega, inverse, nullptr))) return rc;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    CU(cudaMemcpyAsync(limbs, ctx->io.p, n * 96, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaSetDevice(ctx->device));
+    Plan768 *pl;
+    if ((rc = get_plan768(ctx, ilog2(n), omega, inverse, inverse, &pl))) return rc;
+    if ((rc = ensure_io(ctx, n * 96))) return rc;
+    uint32_t *io = (uint32_t *)ctx->io.p;
+    const size_t P = pl->digits.size();
+    cudaStream_t st = ctx->stream;
+    if (P < 2 || n * 96 < (8u << 20)) {  // small: copy in, transform, copy out
+        CU(cudaMemcpyAsync(io, limbs, n * 96, cudaMemcpyHostToDevice, st));
+        if ((rc = launch_ntt768(ctx, pl, io, 1, 0, nullptr, st))) return rc;
+        CU(cudaMemcpyAsync(limbs, io, n * 96, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        return GSN_OK;
+    }
+    // Pipelined: the first pass works on columns of the (2^l_1 x n/2^l_1) view of the input, so the
+    // H2D copy is cut into column blocks (2-D copies) and each block's tiles start as soon as it has
+    // landed; the last pass produces column blocks of the (n/2^l_1 x 2^l_1) view of the output, which
+    // are copied back while later blocks are still being computed.
+    const uint32_t l1 = pl->digits[0], lP = pl->digits[P - 1];
+    const uint64_t cols_in = n >> l1, rows_in = 1ull << l1;     // input view: rows_in x cols_in
+    const uint64_t cols_out = 1ull << l1, rows_out = n >> l1;   // output view: rows_out x cols_out (k1 fastest)
+    const uint64_t tiles = n >> 10;
+    int chunks = 8;
+    while (chunks > 1 && (cols_in % chunks || cols_out % chunks || tiles % chunks || (cols_in / chunks) * rows_in < 1024 ||
+                          (cols_out / chunks) * (1ull << lP) < 1024)) chunks >>= 1;
+    if ((rc = ensure_work(ctx, n * 96))) return rc;
+    CU(cudaEventRecord(ctx->ev0, st));                 // order the copy streams after earlier work on the context
+    CU(cudaStreamWaitEvent(ctx->s_in, ctx->ev0, 0));
+    const uint64_t cw_in = cols_in / chunks, cw_out = cols_out / chunks, tiles_per_chunk = tiles / chunks;
+    for (int c = 0; c < chunks; ++c) {
+        CU(cudaMemcpy2DAsync(io + c * cw_in * 24, cols_in * 96, limbs + c * cw_in * 24, cols_in * 96, cw_in * 96, rows_in, cudaMemcpyHostToDevice, ctx->s_in));
+        CU(cudaEventRecord(ctx->ev_chunk[0][c], ctx->s_in));
+        CU(cudaStreamWaitEvent(st, ctx->ev_chunk[0][c], 0));
+        // pass 1 tiles of this column block: tile t covers sub-transforms (= columns) [t * 2^(10-l1), ...)
+        if ((rc = launch_ntt768_range(ctx, pl, io, 1, 0, nullptr, st, 0, 1, c * tiles_per_chunk, tiles_per_chunk))) return rc;
+    }
+    if (P > 2 && (rc = launch_ntt768_range(ctx, pl, io, 1, 0, nullptr, st, 1, P - 1, 0, 0))) return rc;
+    for (int c = 0; c < chunks; ++c) {
+        // last pass: sub-transform index t = (k_1, k_2, ...) with k_1 most significant, so a contiguous tile
+        // range is a k_1 range = a column block of the output view
+        if ((rc = launch_ntt768_range(ctx, pl, io, 1, 0, nullptr, st, P - 1, P, c * tiles_per_chunk, tiles_per_chunk))) return rc;
+        CU(cudaEventRecord(ctx->ev_chunk[1][c], st));
+        CU(cudaStreamWaitEvent(ctx->s_out, ctx->ev_chunk[1][c], 0));
+        CU(cudaMemcpy2DAsync(limbs + c * cw_out * 24, cols_out * 96, io + c * cw_out * 24, cols_out * 96, cw_out * 96, rows_out, cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    CU(cudaStreamSynchronize(ctx->s_out));
+    CU(cudaStreamSynchronize(st));
     return GSN_OK;
 }
 

@@ -48,6 +48,7 @@ struct PassGeom {
     uint32_t dig[4];         // digit widths l_1..l_P
     uint32_t logn;           // sum of digits
     uint32_t has_pre;        // pre-twiddle table present
+    uint32_t tile0;          // first tile of this launch (chunked launches of one pass)
     uint64_t pre_mask;       // 0 => scalar pre-multiply (pre_tw[0])
 };
 
@@ -109,7 +110,7 @@ ntt768_pass(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, const 
     const uint32_t T = 1u << g.log_tile;
     const uint32_t lq = g.log_l;
     const uint32_t Lm1 = (1u << lq) - 1;
-    const uint64_t sub0 = (uint64_t)blockIdx.x << (g.log_tile - lq);  // first sub-transform of this tile
+    const uint64_t sub0 = (uint64_t)(blockIdx.x + g.tile0) << (g.log_tile - lq);  // first sub-transform of this tile
 
     // ---- load: thread per element, 6 x LDG.128, bit-reversed placement inside its sub-transform
     for (uint32_t e = threadIdx.x; e < T; e += THREADS) {
