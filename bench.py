@@ -181,6 +181,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", type=int, default=0, help="override the transform size (default 20 at N=1, 24 at N>1)")
     ap.add_argument("--cpu-sample-log-n", type=int, default=18)
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N>1: fused = last column pass stores into peer memory over NVLink; nccl = all_to_all_single + repack")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -188,7 +190,9 @@ def main():
     N = max(args.gpus, 1)
     logn = args.log_n or (20 if N == 1 else 24)
     workload = (f"MNT4-753 Fr (768-bit) forward NTT n=2^{logn} on 1xB200" if N == 1 else
-                f"MNT4-753 Fr (768-bit) forward NTT n=2^{logn}, four-step sharded across {N}xB200, NCCL all-to-all")
+                f"MNT4-753 Fr (768-bit) forward NTT n=2^{logn}, four-step sharded across {N}xB200, exchange={args.exchange}"
+                + (" (column-pass epilogue stores tiles into peer HBM over NVLink; NCCL only for two barriers)" if args.exchange == "fused"
+                   else " (NCCL all_to_all_single + repack copy)"))
     config = {"workload": workload, "log_n": logn, "field": "MNT4-753 Fr", "element_bytes": 96,
               "l2": "working set (data + workspace + twiddle table, 3 x n x 96 B) exceeds the 126 MB L2; no flush needed"}
 
@@ -251,12 +255,17 @@ def main():
         passes = max(1, -(-logn // 10))
         kernels_per_step = passes
     else:
-        plan = fourstep.FourStepNTT768(fourstep.CudaBackend(ctx, dev), logn, omega, directions=("forward",))
-        data = synth(plan.column_block_shape())
+        if args.exchange == "fused":
+            plan = fourstep.FusedFourStepNTT768(ctx, dev, logn, omega, directions=("forward",))
+            plan.x.copy_(synth(plan.column_block_shape()))
+            data = plan.x
+        else:
+            plan = fourstep.FourStepNTT768(fourstep.CudaBackend(ctx, dev), logn, omega, directions=("forward",))
+            data = synth(plan.column_block_shape())
         state = {"x": data}
 
         def step():
-            # forward maps column-block -> row-block; feed the output shape back by regenerating a view
+            # forward maps column-block -> row-block (fused: plan.x is only read, plan.y receives the result)
             state["y"] = plan.forward(state["x"])
         local_bytes = data.numel() * 4
         kernels_per_step = None
@@ -294,7 +303,7 @@ def main():
         shard = torch.empty(plan.column_block_shape(), dtype=torch.int32, pin_memory=True)
         shard.copy_(data)
         out_host = torch.empty(plan.row_block_shape(), dtype=torch.int32, pin_memory=True)
-        dbuf = torch.empty_like(data)
+        dbuf = data if args.exchange == "fused" else torch.empty_like(data)
 
         def e2e_step():
             dbuf.copy_(shard, non_blocking=True)
@@ -373,6 +382,10 @@ def main():
                 line["cpu_baseline"] = {"error": str(e)}
         emit(line)
     if world > 1:
+        tm = getattr(plan, "_timing", None) or getattr(plan, "_timing_nccl", None)
+        if tm and rank == 0:
+            calls = tm.pop("calls", 1)
+            print("phase ms:", {k: round(v / calls, 3) for k, v in tm.items()}, file=sys.stderr)
         dist.destroy_process_group()
 
 

@@ -264,7 +264,7 @@ int get_plan768(gsn_ctx *ctx, uint32_t logn, const uint32_t *omega, int inverse,
 
 // Launches passes [q_begin, q_end) of the plan; tile range [tile0, tile0 + ntiles) of each (ntiles == 0: all).
 int launch_ntt768_range(gsn_ctx *ctx, Plan768 *pl, uint32_t *d_data, size_t batch, uint32_t log_r, const uint32_t *ext_pre, cudaStream_t st,
-                        size_t q_begin, size_t q_end, uint64_t tile0, uint64_t ntiles) {
+                        size_t q_begin, size_t q_end, uint64_t tile0, uint64_t ntiles, const gsn::ScatterDesc *scatter = nullptr) {
     const size_t P = pl->digits.size();
     const uint64_t total = (uint64_t)batch << (pl->logn + log_r);
     uint32_t v2 = 0;
@@ -273,6 +273,8 @@ int launch_ntt768_range(gsn_ctx *ctx, Plan768 *pl, uint32_t *d_data, size_t batc
     int rc;
     if (P > 1 && (rc = ensure_work(ctx, total * 96))) return rc;
     uint32_t *work = (uint32_t *)ctx->work.p;
+    gsn::ScatterDesc no_scatter;
+    memset(&no_scatter, 0, sizeof(no_scatter));
 
     auto kern = gsn::ntt768_pass<NTT768_THREADS, 2>;
     if (!ctx->attr768_set) {
@@ -313,7 +315,8 @@ int launch_ntt768_range(gsn_ctx *ctx, Plan768 *pl, uint32_t *d_data, size_t batc
         const uint32_t *src = q == 0 ? d_data : work;
         uint32_t *dst = (q + 1 == P) ? d_data : work;
         const size_t smem = ((size_t)1 << log_tile) * gsn::SMEM_PITCH4 * 16;
-        kern<<<(unsigned)(ntiles ? ntiles : (total >> log_tile)), NTT768_THREADS, smem, st>>>(src, dst, (const uint32_t *)pl->wloc.p, pre, g);
+        kern<<<(unsigned)(ntiles ? ntiles : (total >> log_tile)), NTT768_THREADS, smem, st>>>(src, dst, (const uint32_t *)pl->wloc.p, pre, g,
+                                                                                                         (scatter && q + 1 == P) ? *scatter : no_scatter);
         ctx->launches++;
     }
     CU(cudaGetLastError());
@@ -541,6 +544,61 @@ int gsn_fp768_binop_host(gsn_ctx *ctx, int op, uint32_t *out, const uint32_t *a,
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, dc.p, count * 96, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    return GSN_OK;
+}
+
+int gsn_ntt768_device_scatter(gsn_ctx *ctx, const uint32_t *d_limbs, size_t n, size_t batch, unsigned log_r, const uint32_t *omega,
+                              unsigned flags, const uint32_t *d_pre_table, uint32_t *const *peers, unsigned n_peers, unsigned my_rank,
+                              unsigned rank_shift, unsigned ins_shift, void *stream) {
+    if (!ctx || !d_limbs || !omega || !peers) return fail(GSN_ERR_INVALID_ARG, "null argument");
+    if (n_peers < 1 || n_peers > 8 || (n_peers & (n_peers - 1)) || my_rank >= n_peers) return fail(GSN_ERR_INVALID_ARG, "n_peers = %u, my_rank = %u", n_peers, my_rank);
+    int rc = check_n(n, batch);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    Plan768 *pl;
+    const int inv = (flags & GSN_FLAG_INVERSE_ROOT) != 0, scale = inv && !(flags & GSN_FLAG_NO_SCALE);
+    if (d_pre_table && scale && n <= 1024) return fail(GSN_ERR_INVALID_ARG, "fold the scale into the pre-twiddle table and pass GSN_FLAG_NO_SCALE");
+    if ((rc = get_plan768(ctx, ilog2(n), omega, inv, scale, &pl))) return rc;
+    gsn::ScatterDesc sc;
+    memset(&sc, 0, sizeof(sc));
+    for (unsigned r = 0; r < n_peers; ++r) {
+        if (!peers[r]) return fail(GSN_ERR_INVALID_ARG, "peers[%u] is null", r);
+        sc.peers[r] = peers[r];
+    }
+    sc.enabled = 1;
+    sc.rank_shift = rank_shift;
+    sc.rank_bits = ilog2(n_peers);
+    sc.ins_shift = ins_shift;
+    sc.my_rank = my_rank;
+    // the source is only read: pass 1 goes to the workspace (or, for a one-pass plan, straight to the peers)
+    return launch_ntt768_range(ctx, pl, const_cast<uint32_t *>(d_limbs), batch, log_r, d_pre_table, stream ? (cudaStream_t)stream : ctx->stream, 0,
+                               pl->digits.size(), 0, 0, &sc);
+}
+
+int gsn_ipc_export(gsn_ctx *ctx, void *dptr, unsigned char handle[64]) {
+    if (!ctx || !dptr || !handle) return fail(GSN_ERR_INVALID_ARG, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    CU(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, dptr));
+    memcpy(handle, &h, 64);
+    return GSN_OK;
+}
+
+int gsn_ipc_import(gsn_ctx *ctx, const unsigned char handle[64], void **dptr) {
+    if (!ctx || !dptr || !handle) return fail(GSN_ERR_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return GSN_OK;
+}
+
+int gsn_ipc_close(gsn_ctx *ctx, void *dptr) {
+    if (!ctx) return fail(GSN_ERR_INVALID_ARG, "null ctx");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaIpcCloseMemHandle(dptr));
     return GSN_OK;
 }
 

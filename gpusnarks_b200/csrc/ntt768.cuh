@@ -52,6 +52,23 @@ struct PassGeom {
     uint64_t pre_mask;       // 0 => scalar pre-multiply (pre_tw[0])
 };
 
+// Fused exchange (multi-GPU four-step): the last pass can store each element straight into a
+// peer GPU's buffer over NVLink instead of its own.  The local natural output index is split into
+// three bit fields; the field at [rank_shift, rank_shift + rank_bits) names the destination rank and
+// is replaced, in the destination index, by this rank's id inserted at bit ins_shift of the rest.
+struct ScatterDesc {
+    uint32_t *peers[8];   // peers[r] = base of rank r's receive buffer (own entry = local pointer)
+    uint32_t enabled, rank_shift, rank_bits, ins_shift, my_rank, pad[3];
+};
+
+__device__ __forceinline__ uint32_t *scatter_target(const ScatterDesc &sc, uint64_t go) {
+    const uint32_t dest = (uint32_t)(go >> sc.rank_shift) & ((1u << sc.rank_bits) - 1);
+    const uint64_t rem = ((go >> (sc.rank_shift + sc.rank_bits)) << sc.rank_shift) | (go & ((1ull << sc.rank_shift) - 1));
+    const uint64_t idx = ((rem >> sc.ins_shift) << (sc.ins_shift + sc.rank_bits)) | ((uint64_t)sc.my_rank << sc.ins_shift) |
+                         (rem & ((1ull << sc.ins_shift) - 1));
+    return sc.peers[dest] + idx * NL;
+}
+
 __device__ __forceinline__ uint64_t elem_index(const PassGeom &g, uint64_t t, uint32_t j) {
     const uint64_t o = t >> g.log_s, rlow = t & ((1ull << g.log_s) - 1);
     return (((o << g.log_l) | j) << g.log_s) | rlow;
@@ -105,22 +122,20 @@ __device__ __forceinline__ void sts_elem(uint4 *s, const uint32_t *r) {
 template <int THREADS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 ntt768_pass(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, const uint32_t *__restrict__ wloc,
-            const uint32_t *__restrict__ pre_tw, const PassGeom g) {
+            const uint32_t *__restrict__ pre_tw, const PassGeom g, const ScatterDesc sc) {
     extern __shared__ uint4 tile[];
     const uint32_t T = 1u << g.log_tile;
     const uint32_t lq = g.log_l;
     const uint32_t Lm1 = (1u << lq) - 1;
     const uint64_t sub0 = (uint64_t)(blockIdx.x + g.tile0) << (g.log_tile - lq);  // first sub-transform of this tile
 
-    // ---- load: thread per element, 6 x LDG.128, bit-reversed placement inside its sub-transform
-    for (uint32_t e = threadIdx.x; e < T; e += THREADS) {
+    // ---- load: lane per 16-byte chunk (coalesced 96-byte elements), bit-reversed placement inside the sub-transform
+    for (uint32_t idx = threadIdx.x; idx < T * 6; idx += THREADS) {
+        const uint32_t e = idx / 6, c = idx - e * 6;
         const uint32_t slot = e >> lq, j = e & Lm1;
         const uint64_t gi = elem_index(g, sub0 + slot, j);
-        const uint4 *p = reinterpret_cast<const uint4 *>(src + gi * NL);
         const uint32_t pos = (slot << lq) | (lq ? (__brev(j) >> (32 - lq)) : 0u);
-        uint4 *s = tile + slot_of(pos) * SMEM_PITCH4;
-#pragma unroll
-        for (int c = 0; c < 6; ++c) s[c] = p[c];
+        tile[slot_of(pos) * SMEM_PITCH4 + c] = reinterpret_cast<const uint4 *>(src + gi * NL)[c];
     }
     __syncthreads();
 
@@ -182,21 +197,24 @@ ntt768_pass(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, const 
         __syncthreads();
     }
 
-    // ---- store
-    for (uint32_t e = threadIdx.x; e < T; e += THREADS) {
+    // ---- store: consecutive lanes write consecutive 16-byte chunks of an element, so every warp
+    // store covers whole 96-byte elements (full sectors locally, full packets over NVLink)
+    if (lq == 0 && g.canonical) {  // degenerate n = 1 transforms still leave canonical values
+        for (uint32_t e = threadIdx.x; e < T; e += THREADS) {
+            const uint64_t go = out_index(g, sub0 + e, 0);
+            uint32_t x[NL];
+            lds_elem(x, tile + slot_of(e) * SMEM_PITCH4);
+            canonicalize(x);
+            store_elem(sc.enabled ? scatter_target(sc, go) : dst + go * NL, x);
+        }
+        return;
+    }
+    for (uint32_t idx = threadIdx.x; idx < T * 6; idx += THREADS) {
+        const uint32_t e = idx / 6, c = idx - e * 6;
         const uint32_t slot = e >> lq, k = e & Lm1;
         const uint64_t go = out_index(g, sub0 + slot, k);
-        uint4 *p = reinterpret_cast<uint4 *>(dst + go * NL);
-        const uint4 *s = tile + slot_of(e) * SMEM_PITCH4;
-        if (lq == 0 && g.canonical) {  // degenerate n = 1 transforms still leave canonical values
-            uint32_t x[NL];
-            lds_elem(x, s);
-            canonicalize(x);
-            store_elem(dst + go * NL, x);
-        } else {
-#pragma unroll
-            for (int c = 0; c < 6; ++c) p[c] = s[c];
-        }
+        uint32_t *target = sc.enabled ? scatter_target(sc, go) : dst + go * NL;  // peer memory: plain st.global over NVLink
+        reinterpret_cast<uint4 *>(target)[c] = tile[slot_of(e) * SMEM_PITCH4 + c];
     }
 }
 

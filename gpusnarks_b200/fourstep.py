@@ -21,6 +21,8 @@ The inverse runs the three steps backwards (inverse row NTTs, all-to-all, conjug
 The numerical work is done by a backend object; the product backend is `CudaBackend` (the C
 ABI).  tests/ inject a CPU backend to exercise the exchange logic under gloo.
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -75,6 +77,7 @@ class FourStepNTT768:
         self.w_col = F.mont_pow(self.omega, self.n2, modulus)  # n1-th root
         self.w_row = F.mont_pow(self.omega, self.n1, modulus)  # n2-th root
         self.tw_fwd = self.tw_inv = None
+        self._timing_nccl = {} if os.environ.get("GSN_FOURSTEP_TIMING") else None
         if "forward" in directions:   # rows (rank*R + r), all columns i2
             self.tw_fwd = self.be.table(self.R, self.n2, self.rank * self.R, 0, self.n, self.omega)
         if "inverse" in directions:   # all rows k1, columns rank*C + c; carries n^-1
@@ -97,10 +100,26 @@ class FourStepNTT768:
     def forward(self, x):
         """x: column-block (n1, C, 24) int32, overwritten.  Returns row-block (R, n2, 24)."""
         assert tuple(x.shape) == self.column_block_shape()
+        t = getattr(self, "_timing_nccl", None)
+        if t is not None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            ev[0].record()
         self.be.ntt(x, self.n1, 1, _ilog2(self.C), self.w_col)
+        if t is not None:
+            ev[1].record()
         recv = self._all_to_all(x.view(self.G, self.R, self.C, F.NL))        # [g, r, c]: rows of this rank from every g
+        if t is not None:
+            ev[2].record()
         y = recv.permute(1, 0, 2, 3).contiguous().view(self.R, self.n2, F.NL)  # [r, i2 = g*C + c]
+        if t is not None:
+            ev[3].record()
         self.be.ntt(y, self.n2, self.R, 0, self.w_row, pre_table=self.tw_fwd)
+        if t is not None:
+            ev[4].record()
+            torch.cuda.synchronize()
+            for i, name in enumerate(("column", "all_to_all", "repack", "row")):
+                t[name] = t.get(name, 0.0) + ev[i].elapsed_time(ev[i + 1])
+            t["calls"] = t.get("calls", 0) + 1
         return y
 
     def inverse(self, y):
@@ -133,3 +152,118 @@ def from_row_blocks(blocks, logn, log_n1=None):
     n1, n2 = 1 << log_n1, 1 << (logn - log_n1)
     y = np.concatenate([np.asarray(b) for b in blocks], axis=0)  # (n1, n2, 24) indexed [k1][k2]
     return np.ascontiguousarray(y.transpose(1, 0, 2)).reshape(n1 * n2, F.NL)
+
+
+class _DeviceArray:
+    """wraps library-owned device memory for torch.as_tensor (CUDA array interface)"""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<i4", "data": (int(ptr), False), "version": 3}
+
+
+class FusedFourStepNTT768(FourStepNTT768):
+    """Four-step NTT whose exchange is fused into the transform kernels: the last pass of the
+    column (forward) or row (inverse) transforms stores each output element straight into the
+    destination rank's buffer over NVLink (gsn_ntt768_device_scatter, CUDA-IPC mapped peer
+    memory), so there is no all-to-all and no repacking copy.  NCCL is used only for two
+    stream-ordered barriers per transform (a one-element all-reduce) and for the one-time
+    exchange of the IPC handles.
+
+    The plan owns the two buffers: `self.x` (column-block, (n1, C, 24) int32) and `self.y`
+    (row-block, (R, n2, 24)).  forward(): fill self.x, call, read self.y.  inverse(): the reverse.
+    """
+
+    def __init__(self, ctx, device, logn, omega, group=None, modulus=F.FR, directions=("forward", "inverse"), log_n1=None):
+        super().__init__(CudaBackend(ctx, device), logn, omega, group=group, modulus=modulus, directions=directions, log_n1=log_n1)
+        self.ctx = ctx
+        self.device = device
+        nbytes = self.n1 * self.C * F.NL * 4
+        self._xp = ctx.device_alloc(nbytes)
+        self._yp = ctx.device_alloc(nbytes)
+        self.x = torch.as_tensor(_DeviceArray(self._xp, self.column_block_shape()), device=device)
+        self.y = torch.as_tensor(_DeviceArray(self._yp, self.row_block_shape()), device=device)
+        self._yp2 = ctx.device_alloc(nbytes)  # second receive buffer (forward calls alternate)
+        self.y2 = torch.as_tensor(_DeviceArray(self._yp2, self.row_block_shape()), device=device)
+        self._flip = 1
+        self._timing = {} if os.environ.get("GSN_FOURSTEP_TIMING") else None
+        self._flag = torch.zeros(1, dtype=torch.int32, device=device)
+        self.peers_x, self.peers_y = self._exchange_handles(self._xp), self._exchange_handles(self._yp)
+        self.peers_y2 = self._exchange_handles(self._yp2)
+        self.logG, self.logC, self.logR = _ilog2(self.G), _ilog2(self.C), _ilog2(self.R)
+
+    def _exchange_handles(self, ptr):
+        if self.G == 1:
+            return [ptr]
+        mine = torch.frombuffer(bytearray(self.ctx.ipc_export(ptr)), dtype=torch.uint8).to(self.device)
+        allh = [torch.empty_like(mine) for _ in range(self.G)]
+        dist.all_gather(allh, mine, group=self.group)
+        out = []
+        for r, h in enumerate(allh):
+            out.append(ptr if r == self.rank else self.ctx.ipc_import(bytes(h.cpu().numpy().tobytes())))
+        return out
+
+    def _barrier(self):
+        if self.G > 1:
+            dist.all_reduce(self._flag, group=self.group)  # stream-ordered: later kernels on this stream wait for every rank
+
+    def forward(self, x=None):
+        """column-block self.x -> row-block self.y (returns self.y)"""
+        if x is not None and x.data_ptr() != self.x.data_ptr():
+            self.x.copy_(x)
+        be = self.be
+        t = self._timing
+        if t is not None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
+        # Receive buffers alternate between calls, so the only hazard left is "stores have landed":
+        # a rank that has passed the barrier of call i+1 knows every rank finished the row pass of
+        # call i, hence its buffer of call i may be overwritten by call i+2 without a second barrier.
+        self._flip ^= 1
+        peers_y, yp, y = (self.peers_y, self._yp, self.y) if self._flip == 0 else (self.peers_y2, self._yp2, self.y2)
+        # column NTTs; output element (k1, c) of this rank goes to rank k1 / R, position [k1 % R][rank*C + c]
+        self.ctx.ntt768_device_scatter(self._xp, self.n1, self.w_col, peers_y, self.rank, rank_shift=self.logR + self.logC,
+                                       ins_shift=self.logC, batch=1, log_r=self.logC, stream=be._stream())
+        if t is not None:
+            ev[1].record()
+        self._barrier()  # all stores into y have landed
+        if t is not None:
+            ev[2].record()
+        be.ntt(y, self.n2, self.R, 0, self.w_row, pre_table=self.tw_fwd)
+        if t is not None:
+            ev[3].record()
+            torch.cuda.synchronize(self.device)
+            for i, name in enumerate(("column+scatter", "barrier", "row")):
+                t[name] = t.get(name, 0.0) + ev[i].elapsed_time(ev[i + 1])
+            t["calls"] = t.get("calls", 0) + 1
+        return y
+
+    def inverse(self, y=None):
+        """row-block self.y -> column-block self.x (returns self.x)"""
+        if y is None:
+            y = self.y if self._flip == 0 else self.y2  # the buffer the last forward() filled
+        if y.data_ptr() != self.y.data_ptr():
+            self.y.copy_(y)
+        be = self.be
+        self._barrier()
+        # inverse row NTTs; output element (r, i2) goes to rank i2 / C, position [rank*R + r][i2 % C]
+        self.ctx.ntt768_device_scatter(self._yp, self.n2, self.w_row, self.peers_x, self.rank, rank_shift=self.logC,
+                                       ins_shift=self.logR + self.logC, batch=self.R, log_r=0, inverse_root=True, no_scale=True,
+                                       stream=be._stream())
+        self._barrier()
+        be.ntt(self.x, self.n1, 1, self.logC, self.w_col, inverse_root=True, no_scale=True, pre_table=self.tw_inv)
+        return self.x
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        if self.G > 1:
+            dist.barrier(group=self.group)
+            for r in range(self.G):
+                if r != self.rank:
+                    self.ctx.ipc_close(self.peers_x[r])
+                    self.ctx.ipc_close(self.peers_y[r])
+                    self.ctx.ipc_close(self.peers_y2[r])
+            dist.barrier(group=self.group)
+        self.x = self.y = self.y2 = None
+        self.ctx.device_free(self._xp)
+        self.ctx.device_free(self._yp)
+        self.ctx.device_free(self._yp2)

@@ -116,6 +116,28 @@ class Context:
         self._check(self.L.gsn_ntt768_device_ex(self._h, C.c_void_p(dptr), int(n), int(batch), int(log_r), _ptr(omega), flags,
                                                 C.c_void_p(pre_table or 0), C.c_void_p(stream or 0)))
 
+    def ntt768_device_scatter(self, dptr, n, omega, peers, my_rank, rank_shift, ins_shift, batch=1, log_r=0, inverse_root=False, no_scale=False,
+                              pre_table=None, stream=None):
+        omega = _limbs(omega)
+        flags = (FLAG_INVERSE_ROOT if inverse_root else 0) | (FLAG_NO_SCALE if no_scale else 0)
+        arr = (C.c_void_p * len(peers))(*[C.c_void_p(p) for p in peers])
+        self._check(self.L.gsn_ntt768_device_scatter(self._h, C.c_void_p(dptr), int(n), int(batch), int(log_r), _ptr(omega), flags,
+                                                     C.c_void_p(pre_table or 0), arr, len(peers), int(my_rank), int(rank_shift), int(ins_shift),
+                                                     C.c_void_p(stream or 0)))
+
+    def ipc_export(self, dptr):
+        buf = C.create_string_buffer(64)
+        self._check(self.L.gsn_ipc_export(self._h, C.c_void_p(dptr), buf))
+        return buf.raw
+
+    def ipc_import(self, handle):
+        p = C.c_void_p()
+        self._check(self.L.gsn_ipc_import(self._h, C.c_char_p(handle), C.byref(p)))
+        return p.value
+
+    def ipc_close(self, dptr):
+        self._check(self.L.gsn_ipc_close(self._h, C.c_void_p(dptr)))
+
     def fourstep_table768(self, dptr, rows, cols, row0, col0, n_total, omega, inverse_root=False, scale=False, stream=None):
         omega = _limbs(omega)
         flags = (FLAG_INVERSE_ROOT if inverse_root else 0) | (FLAG_SCALE_TABLE if scale else 0)

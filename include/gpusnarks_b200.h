@@ -91,6 +91,23 @@ int gsn_ntt768_strided_device(gsn_ctx *ctx, uint32_t *d_limbs, size_t n, size_t 
 #define GSN_FLAG_SCALE_TABLE 4u
 int gsn_ntt768_device_ex(gsn_ctx *ctx, uint32_t *d_limbs, size_t n, size_t batch, unsigned log_r,
                          const uint32_t omega[GSN_FP768_LIMBS], unsigned flags, const uint32_t *d_pre_table, void *stream);
+/* Fused transform + exchange for the multi-GPU four-step: like gsn_ntt768_device_ex, but the LAST
+ * pass stores every output element straight into a peer GPU's buffer (plain stores to CUDA-IPC
+ * mapped peer memory, over NVLink) instead of d_limbs, which is only read.  The local natural
+ * output index `go` (over batch x n x 2^log_r) names its destination rank in the bit field
+ * [rank_shift, rank_shift + log2 n_peers); the destination index is `go` with that field removed
+ * and my_rank inserted at bit ins_shift.  peers[r] = base of rank r's receive buffer as mapped
+ * in THIS process (gsn_ipc_import; peers[my_rank] = the local buffer).  n_peers = 1, 2, 4 or 8.
+ * Callers order it against the consumers of the peer buffers (e.g. a stream-ordered barrier). */
+int gsn_ntt768_device_scatter(gsn_ctx *ctx, const uint32_t *d_limbs, size_t n, size_t batch, unsigned log_r,
+                              const uint32_t omega[GSN_FP768_LIMBS], unsigned flags, const uint32_t *d_pre_table,
+                              uint32_t *const *peers, unsigned n_peers, unsigned my_rank, unsigned rank_shift,
+                              unsigned ins_shift, void *stream);
+/* CUDA IPC plumbing for the peer buffers (one process per GPU): export a handle for memory from
+ * gsn_device_alloc, import a peer's handle (enables peer access), close it. */
+int gsn_ipc_export(gsn_ctx *ctx, void *dptr, unsigned char handle[64]);
+int gsn_ipc_import(gsn_ctx *ctx, const unsigned char handle[64], void **dptr);
+int gsn_ipc_close(gsn_ctx *ctx, void *dptr);
 /* d_table[r * cols + c] = omega^(+-(row0 + r) * (col0 + c))  [* n_total^-1 with GSN_FLAG_SCALE_TABLE],
  * r < rows, c < cols, omega a primitive n_total-th root (GSN_FLAG_INVERSE_ROOT: omega^-1):
  * the twiddles between the column and the row transforms of a four-step (Bailey) NTT for

@@ -39,6 +39,17 @@ def main():
             assert (got == O.fft768(a, w, 3)).all(), f"four-step != oracle at 2^{logn}"
         back = plan.inverse(y)
         assert bool((back == x0).all()), f"rank {rank}: inverse(forward) != input at 2^{logn}"
+        # fused exchange (peer stores over NVLink) must give the same bits
+        fplan = fourstep.FusedFourStepNTT768(ctx, dev, logn, w)
+        fplan.x.copy_(x0)
+        yf = fplan.forward()
+        blocks = [torch.empty_like(yf) for _ in range(world)]
+        dist.all_gather(blocks, yf.contiguous())
+        gotf = fourstep.from_row_blocks([b.cpu().numpy().view(np.uint32) for b in blocks], logn)
+        assert (gotf == ref).all(), f"rank {rank}: fused four-step != single-GPU at 2^{logn}"
+        backf = fplan.inverse()
+        assert bool((backf == x0).all()), f"rank {rank}: fused inverse(forward) != input at 2^{logn}"
+        fplan.close()
         dist.barrier()
     if rank == 0:
         print("FOURSTEP_OK", world, "ranks")

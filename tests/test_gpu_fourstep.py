@@ -34,6 +34,30 @@ def test_single_rank_fourstep_vs_oracle(ctx, logn):
     assert bool((back == x0).all())
 
 
+@pytest.mark.parametrize("logn", [6, 12, 16])
+def test_single_rank_fused_fourstep_vs_oracle(ctx, logn):
+    """the scatter-store kernel path with one rank (peer table = the local buffer)"""
+    import torch
+    from gpusnarks_b200 import fourstep
+    dev = torch.device("cuda", 0)
+    n = 1 << logn
+    a = fieldgen.random_elements(n, 177 + logn)
+    w = fieldgen.omega768(n)
+    plan = fourstep.FusedFourStepNTT768(ctx, dev, logn, w)
+    try:
+        x0 = torch.from_numpy(fourstep.to_column_block(a, logn, 1, 0).view(np.int32)).to(dev)
+        plan.x.copy_(x0)
+        y = plan.forward()
+        torch.cuda.synchronize()
+        got = fourstep.from_row_blocks([y.cpu().numpy().view(np.uint32)], logn)
+        assert (got == O.fft768(a, w, 3 if n >= 64 else -1)).all()
+        back = plan.inverse()
+        torch.cuda.synchronize()
+        assert bool((back == x0).all())
+    finally:
+        plan.close()
+
+
 def test_two_rank_fourstep_nccl():
     import torch
     if torch.cuda.device_count() < 2:
