@@ -140,6 +140,22 @@ def cpu_reference_run(sample_logn, steps, warmup):
             "seconds_per_step": sec}
 
 
+def ncu_traffic_bytes(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    summary of one `ncu --set full` capture (profiles/<name>.raw.csv, made by tools/summarize_ncu.py)"""
+    import csv
+    path = os.path.join(ROOT, "profiles", name + ".raw.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = [float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]] for r in rows[2:]]
+        return sum(tot) / len(tot)
+    except Exception:
+        return None
+
+
 def bench_ntt32(ctx, hbm_peak_gbs, logn=22, batch=16, reps=12):
     """BASELINE.json configs[1]: 32-bit prime-field NTT 2^22 on one B200 (HBM-bound).  `batch` distinct
     16 MiB buffers (256 MiB > L2) are transformed per launch pair so that inputs come from HBM; the
@@ -160,7 +176,8 @@ def bench_ntt32(ctx, hbm_peak_gbs, logn=22, batch=16, reps=12):
     return {"workload": f"32-bit prime-field forward NTT n=2^{logn}, p=2013265921, {batch} distinct buffers per launch pair, 1xB200",
             "us_per_transform": t * 1e6, "value": butterflies(logn) / t, "unit": "butterflies/s",
             "roofline": {"kernel": "gsn::ntt32_fast_pass<4,4,3,...>", "bound": "hbm", "achieved": alg / t / 1e9, "peak": hbm_peak_gbs, "unit": "GB/s",
-                         "frac": alg / t / 1e9 / hbm_peak_gbs, "algorithmic_bytes_per_transform": alg, "traffic": None}}
+                         "frac": alg / t / 1e9 / hbm_peak_gbs, "algorithmic_bytes_per_transform": alg,
+                         "traffic": ncu_traffic_bytes("ntt32_fast_pass_r01")}}
 
 
 # ------------------------------------------------------------------------------ main
@@ -356,7 +373,7 @@ def main():
             "int32_issue_rates_per_s": rates["rates"],
             "launches_per_step": kernels_per_step,
             "avg_launch_ms": (ms_step / kernels_per_step) if kernels_per_step else None,
-            "traffic": None,
+            "traffic": ncu_traffic_bytes("ntt768_pass_r01"),
             "hbm": {"algorithmic_bytes_per_step": alg_bytes, "achieved_gbs": (alg_bytes / (ms_step * 1e-3) / 1e9) if alg_bytes else None,
                     "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650"},
         }
