@@ -528,6 +528,72 @@ int gsn_ntt768_time_device(gsn_ctx *ctx, uint32_t *d_limbs, size_t n, size_t bat
     return GSN_OK;
 }
 
+int gsn_fp768_binop_device(gsn_ctx *ctx, int op, uint32_t *d_out, const uint32_t *d_a, const uint32_t *d_b, size_t count, void *stream) {
+    if (!ctx || !d_out || !d_a || !d_b) return fail(GSN_ERR_INVALID_ARG, "null argument");
+    if (op < 0 || op > 2) return fail(GSN_ERR_INVALID_ARG, "op %d", op);
+    if (count == 0) return GSN_OK;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    gsn::binop768<<<(unsigned)((count + 127) / 128), 128, 0, stream ? (cudaStream_t)stream : ctx->stream>>>(d_out, d_a, d_b, count, op);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return GSN_OK;
+}
+
+int gsn_fp768_powers_device(gsn_ctx *ctx, uint32_t *d_table, size_t count, const uint32_t *base, const uint32_t *scale, void *stream) {
+    if (!ctx || !d_table || !base) return fail(GSN_ERR_INVALID_ARG, "null argument");
+    if (count == 0) return GSN_OK;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    DevBuf d_bs;
+    int rc;
+    if ((rc = dev_alloc(d_bs, 192))) return rc;
+    uint32_t h[48];
+    memcpy(h, base, 96);
+    memcpy(h + 24, scale ? scale : ctx->fc.r1, 96);
+    CU(cudaMemcpyAsync(d_bs.p, h, 192, cudaMemcpyHostToDevice, st));
+    gsn::powers768<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(d_table, (const uint32_t *)d_bs.p, (const uint32_t *)d_bs.p + 24, count);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));  // d_bs is freed on return
+    return GSN_OK;
+}
+
+int gsn_fp768_inner_product_device(gsn_ctx *ctx, uint32_t *d_out, const uint32_t *d_a, const uint32_t *d_b, size_t count, void *stream) {
+    if (!ctx || !d_out || !d_a || !d_b) return fail(GSN_ERR_INVALID_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    const unsigned blocks = (unsigned)std::min<size_t>((count + 127) / 128, (size_t)ctx->sm_count * 8);
+    int rc;
+    if ((rc = ensure_work(ctx, (size_t)std::max(1u, blocks) * 96))) return rc;
+    if (count == 0) { CU(cudaMemsetAsync(d_out, 0, 96, st)); return GSN_OK; }
+    gsn::inner_product768<128><<<blocks, 128, 0, st>>>((uint32_t *)ctx->work.p, d_a, d_b, count);
+    gsn::inner_product768<128><<<1, 128, 0, st>>>(d_out, (const uint32_t *)ctx->work.p, nullptr, blocks);
+    ctx->launches += 2;
+    CU(cudaGetLastError());
+    return GSN_OK;
+}
+
+int gsn_fp768_inner_product_host(gsn_ctx *ctx, uint32_t *out, const uint32_t *a, const uint32_t *b, size_t count) {
+    if (!ctx || !out || !a || !b) return fail(GSN_ERR_INVALID_ARG, "null argument");
+    DevBuf da, db, dc;
+    int rc;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        CU(cudaSetDevice(ctx->device));
+        if ((rc = dev_alloc(da, std::max<size_t>(count, 1) * 96)) || (rc = dev_alloc(db, std::max<size_t>(count, 1) * 96)) || (rc = dev_alloc(dc, 96))) return rc;
+        CU(cudaMemcpyAsync(da.p, a, count * 96, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(db.p, b, count * 96, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if ((rc = gsn_fp768_inner_product_device(ctx, (uint32_t *)dc.p, (const uint32_t *)da.p, (const uint32_t *)db.p, count, nullptr))) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaMemcpyAsync(out, dc.p, 96, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GSN_OK;
+}
+
 int gsn_fp768_binop_host(gsn_ctx *ctx, int op, uint32_t *out, const uint32_t *a, const uint32_t *b, size_t count) {
     if (!ctx || !out || !a || !b) return fail(GSN_ERR_INVALID_ARG, "null argument");
     if (op < 0 || op > 2) return fail(GSN_ERR_INVALID_ARG, "op %d", op);

@@ -285,6 +285,78 @@ __global__ void scale_table768(uint32_t *out, const uint32_t *a, const uint32_t 
     store_elem(out + i * NL, r);
 }
 
+// out[i] = scale * base^i (canonical), i < count: coset shifts g^i for coset transforms.
+// Thread i computes base^i by square-and-multiply (tables are built once per domain).
+__global__ void powers768(uint32_t *out, const uint32_t *base, const uint32_t *scale, uint64_t count) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint32_t b[NL], acc[NL];
+    load_elem(b, base);
+    load_elem(acc, scale);
+    const int top = 63 - __clzll((long long)(i | 1));
+    uint32_t r[NL];
+#pragma unroll
+    for (int k = 0; k < NL; ++k) r[k] = c_fp.r1[k];
+    for (int bit = top; bit >= 0; --bit) {
+        uint32_t t[NL];
+        mont_mul_lazy(t, r, r);
+        if ((i >> bit) & 1) mont_mul_lazy(r, t, b);
+        else {
+#pragma unroll
+            for (int k = 0; k < NL; ++k) r[k] = t[k];
+        }
+    }
+    uint32_t o[NL];
+    mont_mul(o, r, acc);
+    store_elem(out + i * NL, o);
+}
+
+// Field inner product sum_i a[i] * b[i]: the reference's multiexp<Scalar, Scalar> (reference
+// cuda/multi_exp.cu:86-137 `deviceReduceKernel` + `deviceReduceKernelSecond`, CPU form test/multiexp.h:3-13).
+// Stage 1: grid-stride products accumulated lazily per thread, block tree reduction in shared memory,
+// one partial per block.  Stage 2 (same kernel, one block, b == nullptr): sums the partials.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) inner_product768(uint32_t *out, const uint32_t *a, const uint32_t *b, uint64_t count) {
+    __shared__ uint4 red[THREADS * 6];
+    uint32_t acc[NL];
+#pragma unroll
+    for (int k = 0; k < NL; ++k) acc[k] = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < count; i += (uint64_t)gridDim.x * THREADS) {
+        uint32_t x[NL], t[NL];
+        load_elem(x, a + i * NL);
+        if (b) {
+            uint32_t y[NL];
+            load_elem(y, b + i * NL);
+            mont_mul_lazy(t, x, y);
+        } else {
+#pragma unroll
+            for (int k = 0; k < NL; ++k) t[k] = x[k];
+        }
+        uint32_t s[NL];
+        add_lazy(s, acc, t);
+#pragma unroll
+        for (int k = 0; k < NL; ++k) acc[k] = s[k];
+    }
+    sts_elem(red + threadIdx.x * 6, acc);
+    __syncthreads();
+    for (int half = THREADS / 2; half >= 1; half >>= 1) {
+        if ((int)threadIdx.x < half) {
+            uint32_t x[NL], y[NL], s[NL];
+            lds_elem(x, red + threadIdx.x * 6);
+            lds_elem(y, red + (threadIdx.x + half) * 6);
+            add_lazy(s, x, y);
+            sts_elem(red + threadIdx.x * 6, s);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        uint32_t x[NL];
+        lds_elem(x, red);
+        canonicalize(x);
+        store_elem(out + (uint64_t)blockIdx.x * NL, x);
+    }
+}
+
 // element-wise field ops for the arithmetic parity tests (canonical results)
 // op: 0 mul, 1 add, 2 sub
 __global__ void binop768(uint32_t *out, const uint32_t *a, const uint32_t *b, uint64_t count, int op) {

@@ -34,6 +34,12 @@ def mont_pow(w_limbs, e, p=FR):
     return to_limbs(pow(w, e, p) * RMONT % p)
 
 
+def mont_inverse(w_limbs, p=FR):
+    """multiplicative inverse, Montgomery form in and out"""
+    w = from_limbs(w_limbs) * pow(RMONT, -1, p) % p
+    return to_limbs(pow(w, -1, p) * RMONT % p)
+
+
 def root_of_unity768(n, p=FR, gen=FR_GENERATOR):
     """primitive n-th root of unity (n a power of two), Montgomery form limbs"""
     assert n >= 1 and n & (n - 1) == 0 and (p - 1) % n == 0

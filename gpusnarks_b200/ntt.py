@@ -161,6 +161,49 @@ class Context:
         self._check(self.L.gsn_fp768_binop_host(self._h, {"mul": 0, "add": 1, "sub": 2}[op], _ptr(out), _ptr(a), _ptr(b), a.shape[0]))
         return out
 
+    def fp768_binop_device(self, op, d_out, d_a, d_b, count, stream=None):
+        self._check(self.L.gsn_fp768_binop_device(self._h, {"mul": 0, "add": 1, "sub": 2}[op], C.c_void_p(d_out), C.c_void_p(d_a), C.c_void_p(d_b),
+                                                  int(count), C.c_void_p(stream or 0)))
+
+    def fp768_powers_device(self, d_table, count, base, scale=None, stream=None):
+        base = _limbs(base)
+        sc = _limbs(scale) if scale is not None else None
+        self._check(self.L.gsn_fp768_powers_device(self._h, C.c_void_p(d_table), int(count), _ptr(base), _ptr(sc) if sc is not None else None,
+                                                   C.c_void_p(stream or 0)))
+
+    def multiexp768(self, a, b):
+        """sum_i a[i] * b[i] -- the reference's multiexp<Scalar, Scalar> (cuda/multi_exp.h:24-25) on host arrays"""
+        a = np.ascontiguousarray(a, dtype=np.uint32).reshape(-1, NL)
+        b = np.ascontiguousarray(b, dtype=np.uint32).reshape(-1, NL)
+        assert a.shape == b.shape
+        out = np.empty(NL, dtype=np.uint32)
+        self._check(self.L.gsn_fp768_inner_product_host(self._h, _ptr(out), _ptr(a), _ptr(b), a.shape[0]))
+        return out
+
+    def coset_ntt768(self, a, omega, shift, inverse=False):
+        """forward: evaluations of the polynomial with coefficients a on the coset shift * <omega>;
+        inverse: coefficients from such evaluations.  Host arrays in/out (device-resident inside)."""
+        from . import field as F
+        a = np.ascontiguousarray(a, dtype=np.uint32).reshape(-1, NL)
+        n = a.shape[0]
+        d = self.device_alloc(a.nbytes)
+        t = self.device_alloc(a.nbytes)
+        try:
+            self.h2d(d, a)
+            if not inverse:
+                self.fp768_powers_device(t, n, shift)
+                self.ntt768_device_ex(d, n, omega, pre_table=t)
+            else:
+                self.ntt768_device(d, n, omega, inverse=True)
+                self.fp768_powers_device(t, n, F.mont_inverse(shift))
+                self.fp768_binop_device("mul", d, d, t, n)
+            out = np.empty_like(a)
+            self.d2h(out, d)
+        finally:
+            self.device_free(d)
+            self.device_free(t)
+        return out
+
     # ---- 32-bit field
     def best_fft32(self, a, omega, mod, inverse=False):
         assert a.dtype == np.uint32 and a.flags["C_CONTIGUOUS"] and a.ndim == 1

@@ -120,6 +120,19 @@ int gsn_fourstep_table768(gsn_ctx *ctx, uint32_t *d_table, size_t rows, size_t c
  * oracle; reference device_field_operators.h:190-214).  op: 0 mul (a*b*R^-1), 1 add, 2 sub. */
 int gsn_fp768_binop_host(gsn_ctx *ctx, int op, uint32_t *out, const uint32_t *a, const uint32_t *b, size_t count);
 
+/* device-resident form of the same element-wise operations (point-wise products between the
+ * transforms of a prover pipeline), stream-ordered */
+int gsn_fp768_binop_device(gsn_ctx *ctx, int op, uint32_t *d_out, const uint32_t *d_a, const uint32_t *d_b, size_t count, void *stream);
+/* d_table[i] = scale * base^i, i < count (scale NULL = one()).  Coset transforms: evaluate on the
+ * coset g<omega> with gsn_ntt768_device_ex(..., d_pre_table = powers(g)); interpolate from it with an
+ * inverse transform followed by gsn_fp768_binop_device(mul, powers(g^-1)). */
+int gsn_fp768_powers_device(gsn_ctx *ctx, uint32_t *d_table, size_t count, const uint32_t base[GSN_FP768_LIMBS],
+                            const uint32_t *scale, void *stream);
+/* sum_i a[i] * b[i] in the field (Montgomery products): the reference's multiexp<Scalar, Scalar>
+ * (reference cuda/multi_exp.h:24-25, cuda/multi_exp.cu:104-137; CPU form test/multiexp.h:3-13). */
+int gsn_fp768_inner_product_device(gsn_ctx *ctx, uint32_t *d_out, const uint32_t *d_a, const uint32_t *d_b, size_t count, void *stream);
+int gsn_fp768_inner_product_host(gsn_ctx *ctx, uint32_t out[GSN_FP768_LIMBS], const uint32_t *a, const uint32_t *b, size_t count);
+
 /* ---- 32-bit NTT over Z/mod (mod an odd prime < 2^31 with n | mod-1).
  * Replaces best_fft for the reference's 32-bit field sketch (fields/dummy_field.h:24-62). */
 int gsn_ntt32_host(gsn_ctx *ctx, uint32_t *a, size_t n, uint32_t omega, uint32_t mod, int inverse);
