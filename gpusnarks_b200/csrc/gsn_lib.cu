@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -82,10 +83,10 @@ struct Plan32 {
     // fast path (two passes, digits of 9..12 stages): in-tile four-step tables per pass and the
     // two-level power tables for the inter-pass twiddle
     bool fast = false;
-    std::vector<std::unique_ptr<DevBuf>> tA, tB;
-    DevBuf t_lo, t_hi, tG;
+    std::vector<std::unique_ptr<DevBuf>> tA, tB, tG;  // per pass
+    DevBuf t_lo, t_lo_scaled, t_hi;                    // two-level powers of w_n (Montgomery-form low tables)
     uint32_t lo_bits = 0;
-    gsn::Ntt32Consts consts;
+    std::vector<gsn::Ntt32Consts> consts;              // per pass
 };
 
 std::vector<uint32_t> plan_digits(uint32_t logn, uint32_t max_log) {

@@ -13,6 +13,9 @@
 // the tile crosses shared memory only twice.  Same index conventions as ntt768.cuh
 // (PassGeom / tools/model_passes.py): output digit order k = k1 + 2^A k2 + 2^(A+B) k3.
 // Arithmetic: canonical residues in [0, p), p < 2^31; twiddle products by Shoup's method.
+// (A persistent one-CTA-per-SM variant that prefetched the next tile with cp.async during rounds
+// B and C was measured ~10 % slower than two independent CTAs per SM -- 32.1 vs 29.3 us at 2^22 --
+// and was removed: the stalls are pipe contention inside the compute phases, not load latency.)
 #pragma once
 #include "ntt32.cuh"
 
@@ -22,10 +25,17 @@ struct Ntt32Consts {
     uint2 rt[8];   // (w, w') for w_16^e, e = 0..7
     uint32_t p;
     uint32_t pinv;           // p^-1 mod 2^32 (Montgomery reduction of the running inter-pass twiddle)
-    uint32_t pre_k_bits;     // inter-pass twiddle w_n^(k * rest): k = sub-transform index mod 2^pre_k_bits
-    uint32_t pre_logn;       // exponents are taken mod 2^pre_logn
-    uint32_t pre_lo_bits;    // two-level split of the exponent
+    // inter-pass twiddle w_N^(k * rest): k = (t >> log_s) mod 2^pre_k_bits (the digit produced by the previous
+    // pass), rest = (j << log_s) | (t mod 2^log_s); exponents mod 2^pre_logN, scaled by 2^pre_exp_shift to w_n
+    uint32_t pre_k_bits, pre_logN, pre_exp_shift;
+    uint32_t pre_lo_bits;    // two-level split of the w_n exponent
+    uint32_t slot_shift;     // the 8 sub-transforms of a tile are 2^slot_shift apart (adjacent OUTPUTS for the last pass)
 };
+
+// first sub-transform of a tile and the step between its 8 slots
+__device__ __forceinline__ uint64_t tile_sub0(uint32_t tile, uint32_t slot_shift) {
+    return ((uint64_t)(tile >> slot_shift) << (slot_shift + 3)) | (tile & ((1u << slot_shift) - 1));
+}
 
 // a * bM * 2^-32 mod p, canonical, for a < 2^32 and bM < p (bM in Montgomery form => plain product a*b)
 __device__ __forceinline__ uint32_t montmul32(uint32_t a, uint32_t bM, uint32_t p, uint32_t pinv) {
@@ -47,9 +57,9 @@ __device__ __forceinline__ void ntt_reg(uint32_t *r, const Ntt32Consts &c) {
             for (int j = 0; j < half; ++j) {
                 const uint32_t u = r[base + j], v = r[base + j + half];
                 r[base + j] = addmod(u, v, c.p);
-                const uint32_t d = submod(u, v, c.p);
                 const int e = j * (8 / half);  // w_16^(j * 16 / (2 half))
-                r[base + j + half] = e == 0 ? d : mulmod_shoup(d, c.rt[e], c.p);
+                // the Shoup product accepts any 32-bit operand, so u - v + p (in (0, 2p)) needs no reduction first
+                r[base + j + half] = e == 0 ? submod(u, v, c.p) : mulmod_shoup(u - v + c.p, c.rt[e], c.p);
             }
         }
     }
@@ -84,7 +94,8 @@ ntt32_fast_pass(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, co
                 const uint2 *__restrict__ tG, const PassGeom g, const Ntt32Consts c) {
     using T = FastTile<A, B, C>;
     extern __shared__ uint32_t sm[];
-    const uint64_t sub0 = (uint64_t)blockIdx.x * T::SLOTS;
+    const uint64_t sub0 = tile_sub0(blockIdx.x, c.slot_shift);
+    const uint32_t ss = c.slot_shift;
     const uint32_t p = c.p;
 
     // ---------------- round A: global -> registers -> shared
@@ -93,18 +104,20 @@ ntt32_fast_pass(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, co
         uint32_t s, q;
         if (SLOT_FAST) { s = item & 7; q = item >> 3; } else { q = item & (T::QA - 1); s = item >> (B + C); }
         // element (sub-transform t, index j) lives at base + (j << log_s): linear in j
-        const uint32_t *in = src + elem_index(g, sub0 + s, q);
+        const uint64_t t = sub0 + ((uint64_t)s << ss);
+        const uint32_t *in = src + elem_index(g, t, q);
         const uint64_t jstride = (uint64_t)T::QA << g.log_s;
         uint32_t r[1 << A];
 #pragma unroll
         for (int j1 = 0; j1 < (1 << A); ++j1) r[j1] = in[j1 * jstride];
         if (PRE) {
-            // inter-pass twiddle w_n^(k * (j1*QA + q)) = w^(k q) * (w^(k QA))^j1: one two-level lookup for
-            // the first factor, then a geometric recurrence.  The running twiddle is kept in Montgomery
-            // form (t_lo holds w^e * [n^-1] * 2^32), so stepping it is a Shoup product by the per-row
-            // constant tG[k] and applying it is a Montgomery product.
-            const uint32_t k = (uint32_t)(sub0 + s) & ((1u << c.pre_k_bits) - 1);
-            const uint32_t e0 = (k * q) & ((1u << c.pre_logn) - 1);
+            // inter-pass twiddle w_N^(k * rest(j1)), rest(j1) = ((j1*QA + q) << log_s) | rlow: the first factor
+            // w^(k * rest(0)) is one two-level table lookup, the rest a geometric recurrence with the per-k
+            // step tG[k] = w_N^(k * (QA << log_s)).  The running twiddle is kept in Montgomery form (t_lo holds
+            // w^e * [n^-1] * 2^32), so stepping it is a Shoup product and applying it a Montgomery product.
+            const uint32_t k = (uint32_t)(t >> g.log_s) & ((1u << c.pre_k_bits) - 1);
+            const uint32_t rest0 = (q << g.log_s) | ((uint32_t)t & ((1u << g.log_s) - 1));
+            const uint32_t e0 = ((k * rest0) & ((1u << c.pre_logN) - 1)) << c.pre_exp_shift;
             uint32_t tw = mulmod_shoup(__ldg(t_lo + (e0 & ((1u << c.pre_lo_bits) - 1))).x, __ldg(t_hi + (e0 >> c.pre_lo_bits)), p);
             const uint2 step = __ldg(tG + k);
 #pragma unroll
@@ -150,8 +163,9 @@ ntt32_fast_pass(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, co
         }
         ntt_reg<C>(r, c);
         // the output index is linear in k as well: out(k) = out(kk) + k3 * kstride
-        const uint64_t o0 = out_index(g, sub0 + s, kk);
-        const uint64_t kstride = out_index(g, sub0 + s, kk + (1u << (A + B))) - o0;
+        const uint64_t t = sub0 + ((uint64_t)s << ss);
+        const uint64_t o0 = out_index(g, t, kk);
+        const uint64_t kstride = out_index(g, t, kk + (1u << (A + B))) - o0;
 #pragma unroll
         for (int k3 = 0; k3 < (1 << C); ++k3) dst[o0 + k3 * kstride] = r[k3];
     }

@@ -52,7 +52,9 @@ int get_plan32(gsn_ctx *ctx, uint32_t logn, uint32_t omega, uint32_t mod, int in
     if ((rc = dev_alloc(pl->wloc, half * 8))) return rc;
     gsn::pow_table32<<<(unsigned)((half + 255) / 256), 256, 0, st>>>((uint2 *)pl->wloc.p, w_eff, half, pl->lmax ? (n >> pl->lmax) : 0, 1, mod);
     ctx->launches++;
-    pl->fast = P == 2 && pl->digits[0] >= 9 && pl->digits[0] <= 12 && pl->digits[1] >= 9 && pl->digits[1] <= 12;
+    // fast path: every digit has 8..12 stages (n >= 2^16) -> register-blocked in-tile four-step kernels
+    pl->fast = P >= 2 && P <= 4;
+    for (size_t q = 0; q < P; ++q) pl->fast = pl->fast && pl->digits[q] >= 8 && pl->digits[q] <= 12;
     if (P > 1) {
         const uint32_t lo_bits = std::min<uint32_t>(11, logn);
         pl->lo_bits = lo_bits;
@@ -61,14 +63,27 @@ int get_plan32(gsn_ctx *ctx, uint32_t logn, uint32_t omega, uint32_t mod, int in
         gsn::pow_table32<<<(unsigned)((n >> lo_bits) + 255) / 256, 256, 0, st>>>((uint2 *)t_hi.p, w_eff, n >> lo_bits, 1ull << lo_bits, 1, mod);
         ctx->launches++;
         if (pl->fast) {
-            // in-tile four-step tables (unscaled low table), then the low table is rebuilt carrying n^-1
+            auto split = [](uint32_t L, uint32_t &a, uint32_t &b, uint32_t &c) {
+                a = L >= 10 ? 4 : 3;
+                c = L == 12 ? 4 : (L == 8 ? 2 : 3);
+                b = L - a - c;
+            };
+            // in-tile four-step tables from the plain low table
             gsn::pow_table32<<<(unsigned)(((1ull << lo_bits) + 255) / 256), 256, 0, st>>>((uint2 *)t_lo.p, w_eff, 1ull << lo_bits, 1, 1, mod);
             ctx->launches++;
             pl->tA.resize(P);
             pl->tB.resize(P);
+            pl->tG.resize(P);
+            pl->consts.resize(P);
+            uint32_t inv = 1;  // Newton: p^-1 mod 2^32
+            for (int i = 0; i < 5; ++i) inv *= 2 - mod * inv;
+            const uint32_t w16 = powmod_h(w_eff, n >> 4, mod);
+            uint32_t below = logn;
             for (size_t q = 0; q < P; ++q) {
                 const uint32_t L = pl->digits[q];
-                const uint32_t a = L >= 10 ? 4 : 3, c = L == 12 ? 4 : 3, b = L - a - c;
+                below -= L;  // log2 stride of this digit
+                uint32_t a, b, c;
+                split(L, a, b, c);
                 pl->tA[q] = std::make_unique<DevBuf>();
                 pl->tB[q] = std::make_unique<DevBuf>();
                 if ((rc = dev_alloc(*pl->tA[q], (1ull << L) * 8)) || (rc = dev_alloc(*pl->tB[q], (1ull << (b + c)) * 8))) return rc;
@@ -77,37 +92,41 @@ int get_plan32(gsn_ctx *ctx, uint32_t logn, uint32_t omega, uint32_t mod, int in
                 gsn::build_pretw32<<<(unsigned)(((1ull << (b + c)) + 255) / 256), 256, 0, st>>>((uint2 *)pl->tB[q]->p, (const uint2 *)t_lo.p, (const uint2 *)t_hi.p,
                                                                                                b + c, c, logn - (b + c), lo_bits, mod);
                 ctx->launches += 2;
-            }
-            // low table of the inter-pass twiddle: w^e * n^-1 (inverse plans) * 2^32, i.e. Montgomery form
-            const uint32_t r32 = (uint32_t)((1ull << 32) % mod);
-            gsn::pow_table32<<<(unsigned)(((1ull << lo_bits) + 255) / 256), 256, 0, st>>>((uint2 *)t_lo.p, w_eff, 1ull << lo_bits, 1, mulmod_h(n_inv, r32, mod), mod);
-            // per-row step of the recurrence in pass 2: tG[k] = w^(k * QA), QA = 2^(B+C) of the second digit
-            {
-                const uint32_t L2 = pl->digits[1];
-                const uint32_t a2 = L2 >= 10 ? 4 : 3;
-                const uint64_t rows = 1ull << pl->digits[0];
-                if ((rc = dev_alloc(pl->tG, rows * 8))) return rc;
-                gsn::pow_table32<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>((uint2 *)pl->tG.p, powmod_h(w_eff, 1ull << (L2 - a2), mod), rows, 1, 1, mod);
-            }
-            ctx->launches += 2;
-            pl->pre_mask[1] = n - 1;
-            gsn::Ntt32Consts &k = pl->consts;
-            memset(&k, 0, sizeof(k));
-            const uint32_t w16 = powmod_h(w_eff, n >> 4, mod);
-            uint32_t acc = 1;
-            for (int e = 0; e < 8; ++e) {
-                k.rt[e] = make_uint2(acc, (uint32_t)(((uint64_t)acc << 32) / mod));
-                acc = mulmod_h(acc, w16, mod);
-            }
-            k.p = mod;
-            {
-                uint32_t inv = 1;  // Newton: p^-1 mod 2^32
-                for (int i = 0; i < 5; ++i) inv *= 2 - mod * inv;
+                gsn::Ntt32Consts &k = pl->consts[q];
+                memset(&k, 0, sizeof(k));
+                uint32_t acc = 1;
+                for (int e = 0; e < 8; ++e) {
+                    k.rt[e] = make_uint2(acc, (uint32_t)(((uint64_t)acc << 32) / mod));
+                    acc = mulmod_h(acc, w16, mod);
+                }
+                k.p = mod;
                 k.pinv = inv;
+                k.pre_lo_bits = lo_bits;
+                // the last pass groups sub-transforms whose OUTPUTS are adjacent: k_1 varies fastest in the output
+                k.slot_shift = (q + 1 == P && P > 2) ? (logn - pl->digits[0] - L) : 0;
+                if (q >= 1) {
+                    // boundary q: w_N^(k * rest), N = 2^(l_{q-1} + ... + l_P), k = digit q-1, rest = (digit q.. | )
+                    uint32_t logN = 0;
+                    for (size_t i = q - 1; i < P; ++i) logN += pl->digits[i];
+                    k.pre_k_bits = pl->digits[q - 1];
+                    k.pre_logN = logN;
+                    k.pre_exp_shift = logn - logN;
+                    pl->pre_mask[q] = (1ull << logN) - 1;
+                    // per-k step of the recurrence along the 2^a elements a thread holds: w_N^(k * (QA << log_s))
+                    const uint64_t rows = 1ull << k.pre_k_bits;
+                    pl->tG[q] = std::make_unique<DevBuf>();
+                    if ((rc = dev_alloc(*pl->tG[q], rows * 8))) return rc;
+                    const uint64_t step_e = ((1ull << (L - a)) << below) << k.pre_exp_shift;  // exponent of w_n
+                    gsn::pow_table32<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>((uint2 *)pl->tG[q]->p, powmod_h(w_eff, step_e, mod), rows, 1, 1, mod);
+                    ctx->launches++;
+                }
             }
-            k.pre_k_bits = pl->digits[0];
-            k.pre_logn = logn;
-            k.pre_lo_bits = lo_bits;
+            // low tables of the inter-pass twiddles in Montgomery form (x 2^32); boundary 1 also carries n^-1
+            const uint32_t r32 = (uint32_t)((1ull << 32) % mod);
+            if ((rc = dev_alloc(pl->t_lo_scaled, (1ull << lo_bits) * 8))) return rc;
+            gsn::pow_table32<<<(unsigned)(((1ull << lo_bits) + 255) / 256), 256, 0, st>>>((uint2 *)pl->t_lo_scaled.p, w_eff, 1ull << lo_bits, 1, mulmod_h(n_inv, r32, mod), mod);
+            gsn::pow_table32<<<(unsigned)(((1ull << lo_bits) + 255) / 256), 256, 0, st>>>((uint2 *)t_lo.p, w_eff, 1ull << lo_bits, 1, r32, mod);
+            ctx->launches += 2;
         } else {
             for (size_t q = P - 1; q >= 1; --q) {
                 uint32_t logN = 0;
@@ -155,6 +174,7 @@ template <bool SLOT_FAST, bool PRE>
 int dispatch_fast32(uint32_t L, gsn_ctx *ctx, unsigned grid, cudaStream_t st, const uint32_t *src, uint32_t *dst, const uint2 *tA,
                     const uint2 *tB, const uint2 *t_lo, const uint2 *t_hi, const uint2 *tG, const gsn::PassGeom &g, const gsn::Ntt32Consts &k) {
     switch (L) {
+        case 8: return launch_fast32<3, 3, 2, SLOT_FAST, PRE>(ctx, grid, st, src, dst, tA, tB, t_lo, t_hi, tG, g, k);
         case 9: return launch_fast32<3, 3, 3, SLOT_FAST, PRE>(ctx, grid, st, src, dst, tA, tB, t_lo, t_hi, tG, g, k);
         case 10: return launch_fast32<4, 3, 3, SLOT_FAST, PRE>(ctx, grid, st, src, dst, tA, tB, t_lo, t_hi, tG, g, k);
         case 11: return launch_fast32<4, 4, 3, SLOT_FAST, PRE>(ctx, grid, st, src, dst, tA, tB, t_lo, t_hi, tG, g, k);
@@ -163,28 +183,35 @@ int dispatch_fast32(uint32_t L, gsn_ctx *ctx, unsigned grid, cudaStream_t st, co
 }
 
 int launch_ntt32_fast(gsn_ctx *ctx, Plan32 *pl, uint32_t *d_data, size_t batch, cudaStream_t st) {
+    const size_t P = pl->digits.size();
     const uint64_t total = (uint64_t)batch << pl->logn;
     int rc;
     if ((rc = ensure_work(ctx, total * 4))) return rc;
     uint32_t *work = (uint32_t *)ctx->work.p;
-    for (size_t q = 0; q < 2; ++q) {
+    uint32_t below = pl->logn;
+    for (size_t q = 0; q < P; ++q) {
+        below -= pl->digits[q];
         gsn::PassGeom g;
         memset(&g, 0, sizeof(g));
         g.log_l = pl->digits[q];
-        g.log_s = q == 0 ? pl->digits[1] : 0;
-        g.final_natural = q == 1;
+        g.log_s = below;
+        g.final_natural = q + 1 == P;
         g.canonical = 1;
-        g.ndig = 2;
-        g.dig[0] = pl->digits[0];
-        g.dig[1] = pl->digits[1];
+        g.ndig = (uint32_t)P;
+        for (size_t i = 0; i < P; ++i) g.dig[i] = pl->digits[i];
         g.logn = pl->logn;
-        g.has_pre = q == 1;
+        g.has_pre = q >= 1;
         g.pre_mask = pl->pre_mask[q];
         const unsigned grid = (unsigned)((total >> g.log_l) / 8);
         const uint2 *tA = (const uint2 *)pl->tA[q]->p, *tB = (const uint2 *)pl->tB[q]->p;
-        const uint2 *t_lo = (const uint2 *)pl->t_lo.p, *t_hi = (const uint2 *)pl->t_hi.p, *tG = (const uint2 *)pl->tG.p;
-        if (q == 0) rc = dispatch_fast32<true, false>(g.log_l, ctx, grid, st, d_data, work, tA, tB, t_lo, t_hi, tG, g, pl->consts);
-        else rc = dispatch_fast32<false, true>(g.log_l, ctx, grid, st, work, d_data, tA, tB, t_lo, t_hi, tG, g, pl->consts);
+        const uint2 *t_lo = (const uint2 *)(q == 1 ? pl->t_lo_scaled.p : pl->t_lo.p), *t_hi = (const uint2 *)pl->t_hi.p;
+        const uint2 *tG = q >= 1 ? (const uint2 *)pl->tG[q]->p : nullptr;
+        // pass 1 reads the caller's buffer, the last pass writes it, middle passes run in place in the workspace
+        const uint32_t *src = q == 0 ? d_data : work;
+        uint32_t *dst = (q + 1 == P) ? d_data : work;
+        if (q == 0) rc = dispatch_fast32<true, false>(g.log_l, ctx, grid, st, src, dst, tA, tB, t_lo, t_hi, tG, g, pl->consts[q]);
+        else if (q + 1 < P) rc = dispatch_fast32<true, true>(g.log_l, ctx, grid, st, src, dst, tA, tB, t_lo, t_hi, tG, g, pl->consts[q]);
+        else rc = dispatch_fast32<false, true>(g.log_l, ctx, grid, st, src, dst, tA, tB, t_lo, t_hi, tG, g, pl->consts[q]);
         if (rc) return rc;
     }
     CU(cudaGetLastError());

@@ -60,7 +60,7 @@ def test_edge_values(ctx):
 
 
 def test_batched_device(ctx):
-    for logn, batch in [(4, 7), (11, 3), (12, 2), (16, 3), (22, 2)]:
+    for logn, batch in [(4, 7), (11, 3), (12, 2), (16, 3), (17, 5), (22, 2)]:
         n = 1 << logn
         a = fieldgen.random_u32(batch * n, 9 + logn, P)
         w = fieldgen.omega32(n)
@@ -102,8 +102,9 @@ def test_golden_fixtures(ctx):
         assert hashlib.sha256(out.tobytes()).hexdigest() == case["sha256"], case
 
 
-@pytest.mark.parametrize("logn", [24, 26])
+@pytest.mark.parametrize("logn", [23, 24, 25, 26, 27])
 def test_large_properties(ctx, logn):
+    """two-pass (<= 2^24) and three-pass (2^25..2^27, digits of 8 and 9 stages) fast-path sizes"""
     n = 1 << logn
     a = fieldgen.random_u32(n, 70 + logn, P)
     w = fieldgen.omega32(n)
