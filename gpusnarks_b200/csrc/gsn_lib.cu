@@ -16,6 +16,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/gpusnarks_b200.h"
@@ -121,6 +122,7 @@ struct gsn_ctx {
     cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the pipelined host-pointer path
     cudaEvent_t ev_chunk[2][16] = {{nullptr}};
     bool attr768_set = false, attr32_set = false;
+    std::unordered_set<const void *> smem_configured;  // kernels whose dynamic shared-memory limit was raised on this device
 };
 
 namespace {
@@ -641,6 +643,23 @@ int gsn_ntt768_device_scatter(gsn_ctx *ctx, const uint32_t *d_limbs, size_t n, s
     // the source is only read: pass 1 goes to the workspace (or, for a one-pass plan, straight to the peers)
     return launch_ntt768_range(ctx, pl, const_cast<uint32_t *>(d_limbs), batch, log_r, d_pre_table, stream ? (cudaStream_t)stream : ctx->stream, 0,
                                pl->digits.size(), 0, 0, &sc);
+}
+
+int gsn_peer_barrier(gsn_ctx *ctx, uint32_t *const *peer_flags, unsigned n_peers, unsigned my_rank, unsigned epoch, void *stream) {
+    if (!ctx || !peer_flags) return fail(GSN_ERR_INVALID_ARG, "null argument");
+    if (n_peers < 1 || n_peers > 8 || my_rank >= n_peers) return fail(GSN_ERR_INVALID_ARG, "n_peers = %u, my_rank = %u", n_peers, my_rank);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    gsn::PeerFlags pf;
+    memset(&pf, 0, sizeof(pf));
+    for (unsigned r = 0; r < n_peers; ++r) {
+        if (!peer_flags[r]) return fail(GSN_ERR_INVALID_ARG, "peer_flags[%u] is null", r);
+        pf.flags[r] = peer_flags[r];
+    }
+    gsn::peer_barrier_kernel<<<1, 32, 0, stream ? (cudaStream_t)stream : ctx->stream>>>(pf, n_peers, my_rank, epoch);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return GSN_OK;
 }
 
 int gsn_ipc_export(gsn_ctx *ctx, void *dptr, unsigned char handle[64]) {

@@ -160,10 +160,9 @@ int launch_fast32(gsn_ctx *ctx, unsigned grid, cudaStream_t st, const uint32_t *
                   const uint2 *t_lo, const uint2 *t_hi, const uint2 *tG, const gsn::PassGeom &g, const gsn::Ntt32Consts &k) {
     constexpr int MINB = (A + B + C) == 12 ? 1 : 2;
     auto kern = gsn::ntt32_fast_pass<A, B, C, SLOT_FAST, PRE, MINB>;
-    static bool attr_done = false;  // per instantiation; one device per process in this library's deployment model
-    if (!attr_done) {
+    if (!ctx->smem_configured.count((const void *)kern)) {  // function attributes are per device, i.e. per context
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsn::FastTile<A, B, C>::SMEM_BYTES));
-        attr_done = true;
+        ctx->smem_configured.insert((const void *)kern);
     }
     kern<<<grid, 512, gsn::FastTile<A, B, C>::SMEM_BYTES, st>>>(src, dst, tA, tB, t_lo, t_hi, tG, g, k);
     ctx->launches++;

@@ -69,6 +69,34 @@ __device__ __forceinline__ uint32_t *scatter_target(const ScatterDesc &sc, uint6
     return sc.peers[dest] + idx * NL;
 }
 
+// Barrier across the GPUs of a four-step transform, in peer memory: lane r publishes `epoch` into slot
+// [my_rank] of rank r's flag array (release at system scope: everything this GPU stored before the kernel
+// boundary -- the scattered tiles -- is visible to whoever acquires the flag), then waits until rank r has
+// published the same epoch into slot [r] of the local array.  A peer that never arrives traps after
+// ~10 s instead of hanging the device.
+struct PeerFlags {
+    uint32_t *flags[8];   // flags[r] = rank r's array of 8 slots (own entry = local array)
+};
+
+__global__ void peer_barrier_kernel(const PeerFlags pf, uint32_t n_peers, uint32_t my_rank, uint32_t epoch) {
+    const uint32_t r = threadIdx.x;
+    if (r >= n_peers) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pf.flags[r] + my_rank), "r"(epoch) : "memory");
+    const uint32_t *mine = pf.flags[my_rank] + r;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+        if ((int32_t)(v - epoch) >= 0) break;
+        __nanosleep(200);
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 10000000000ull) __trap();
+    }
+}
+
 __device__ __forceinline__ uint64_t elem_index(const PassGeom &g, uint64_t t, uint32_t j) {
     const uint64_t o = t >> g.log_s, rlow = t & ((1ull << g.log_s) - 1);
     return (((o << g.log_l) | j) << g.log_s) | rlow;

@@ -187,8 +187,16 @@ class FusedFourStepNTT768(FourStepNTT768):
         self._flip = 1
         self._timing = {} if os.environ.get("GSN_FOURSTEP_TIMING") else None
         self._flag = torch.zeros(1, dtype=torch.int32, device=device)
+        # flag array for the peer-memory barrier (8 slots), zeroed before anyone can signal it
+        self._fp = ctx.device_alloc(256)
+        ctx.h2d(self._fp, np.zeros(64, dtype=np.uint32))
+        self._epoch = 0
+        self._nccl_barrier = bool(os.environ.get("GSN_FOURSTEP_NCCL_BARRIER"))
         self.peers_x, self.peers_y = self._exchange_handles(self._xp), self._exchange_handles(self._yp)
         self.peers_y2 = self._exchange_handles(self._yp2)
+        self.peer_flags = self._exchange_handles(self._fp)
+        if self.G > 1:
+            dist.barrier(group=self.group)  # every rank has zeroed and published its flags
         self.logG, self.logC, self.logR = _ilog2(self.G), _ilog2(self.C), _ilog2(self.R)
 
     def _exchange_handles(self, ptr):
@@ -203,8 +211,14 @@ class FusedFourStepNTT768(FourStepNTT768):
         return out
 
     def _barrier(self):
-        if self.G > 1:
-            dist.all_reduce(self._flag, group=self.group)  # stream-ordered: later kernels on this stream wait for every rank
+        """stream-ordered barrier across the ranks: later kernels on this stream start after every rank got here"""
+        if self.G == 1:
+            return
+        if self._nccl_barrier:
+            dist.all_reduce(self._flag, group=self.group)
+        else:
+            self._epoch += 1
+            self.ctx.peer_barrier(self.peer_flags, self.rank, self._epoch, stream=self.be._stream())
 
     def forward(self, x=None):
         """column-block self.x -> row-block self.y (returns self.y)"""
@@ -262,8 +276,10 @@ class FusedFourStepNTT768(FourStepNTT768):
                     self.ctx.ipc_close(self.peers_x[r])
                     self.ctx.ipc_close(self.peers_y[r])
                     self.ctx.ipc_close(self.peers_y2[r])
+                    self.ctx.ipc_close(self.peer_flags[r])
             dist.barrier(group=self.group)
         self.x = self.y = self.y2 = None
         self.ctx.device_free(self._xp)
         self.ctx.device_free(self._yp)
         self.ctx.device_free(self._yp2)
+        self.ctx.device_free(self._fp)

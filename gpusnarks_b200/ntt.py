@@ -125,6 +125,10 @@ class Context:
                                                      C.c_void_p(pre_table or 0), arr, len(peers), int(my_rank), int(rank_shift), int(ins_shift),
                                                      C.c_void_p(stream or 0)))
 
+    def peer_barrier(self, peer_flags, my_rank, epoch, stream=None):
+        arr = (C.c_void_p * len(peer_flags))(*[C.c_void_p(p) for p in peer_flags])
+        self._check(self.L.gsn_peer_barrier(self._h, arr, len(peer_flags), int(my_rank), int(epoch) & 0xFFFFFFFF, C.c_void_p(stream or 0)))
+
     def ipc_export(self, dptr):
         buf = C.create_string_buffer(64)
         self._check(self.L.gsn_ipc_export(self._h, C.c_void_p(dptr), buf))

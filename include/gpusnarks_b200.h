@@ -103,6 +103,11 @@ int gsn_ntt768_device_scatter(gsn_ctx *ctx, const uint32_t *d_limbs, size_t n, s
                               const uint32_t omega[GSN_FP768_LIMBS], unsigned flags, const uint32_t *d_pre_table,
                               uint32_t *const *peers, unsigned n_peers, unsigned my_rank, unsigned rank_shift,
                               unsigned ins_shift, void *stream);
+/* Stream-ordered barrier across the ranks of a four-step transform, in peer memory (no NCCL on the
+ * hot path): peer_flags[r] = rank r's array of 8 zero-initialised uint32 slots as mapped in this
+ * process.  The kernel publishes `epoch` (must increase by one per call, same on all ranks) with
+ * release semantics at system scope and waits for every peer's epoch; it traps after ~10 s. */
+int gsn_peer_barrier(gsn_ctx *ctx, uint32_t *const *peer_flags, unsigned n_peers, unsigned my_rank, unsigned epoch, void *stream);
 /* CUDA IPC plumbing for the peer buffers (one process per GPU): export a handle for memory from
  * gsn_device_alloc, import a peer's handle (enables peer access), close it. */
 int gsn_ipc_export(gsn_ctx *ctx, void *dptr, unsigned char handle[64]);
