@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(HERE, "libgpusnarks_b200.so")
 # every symbol include/gpusnarks_b200.h declares (tests check that the .so exports them all)
 SYMBOLS = [
     "gsn_ctx_create", "gsn_ctx_destroy", "gsn_last_error", "gsn_set_field768", "gsn_ctx_trim", "gsn_launch_count",
-    "gsn_ntt768_host", "gsn_ntt768_device", "gsn_ntt768_prepare", "gsn_ntt768_strided_device",
+    "gsn_ntt768_host", "gsn_ntt768_host_batch", "gsn_ntt768_device", "gsn_ntt768_prepare", "gsn_ntt768_strided_device",
     "gsn_ntt768_device_ex", "gsn_fourstep_table768", "gsn_ntt768_device_scatter", "gsn_peer_barrier", "gsn_ipc_export", "gsn_ipc_import", "gsn_ipc_close", "gsn_fp768_binop_host", "gsn_fp768_binop_device", "gsn_fp768_powers_device", "gsn_fp768_inner_product_device", "gsn_fp768_inner_product_host", "gsn_ntt32_host", "gsn_ntt32_device",
     "gsn_device_count", "gsn_host_alloc", "gsn_host_free", "gsn_device_alloc", "gsn_device_free",
     "gsn_memcpy_h2d", "gsn_memcpy_d2h", "gsn_ctx_synchronize", "gsn_int32_issue_rates",
@@ -36,6 +36,7 @@ def load():
     L.gsn_ctx_trim.argtypes = [vp]
     L.gsn_launch_count.argtypes = [vp, u64p]
     L.gsn_ntt768_host.argtypes = [vp, u32p, sz, u32p, i]
+    L.gsn_ntt768_host_batch.argtypes = [vp, C.POINTER(vp), sz, sz, u32p, i]
     L.gsn_ntt768_device.argtypes = [vp, vp, sz, sz, u32p, i, vp]
     L.gsn_ntt768_prepare.argtypes = [vp, sz, sz, u32p, i]
     L.gsn_ntt768_strided_device.argtypes = [vp, vp, sz, sz, C.c_uint, u32p, i, vp]

@@ -114,6 +114,8 @@ struct gsn_ctx {
     int two_adicity = 30;
     DevBuf work;
     DevBuf io;   // device staging buffer of the host-pointer entry points (grown on demand, reused)
+    DevBuf io2;  // second staging buffer: the batch entry point alternates between the two
+    cudaEvent_t ev_io_free[2] = {nullptr, nullptr};  // D2H of the transform that last used io / io2 has finished
     std::vector<std::unique_ptr<Plan768>> plans768;
     std::vector<std::unique_ptr<Plan32>> plans32;
     uint64_t launches = 0;
@@ -375,6 +377,7 @@ int gsn_ctx_create(gsn_ctx **out, int device) {
     CU(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
     for (int d = 0; d < 2; ++d)
         for (int i = 0; i < 16; ++i) CU(cudaEventCreateWithFlags(&ctx->ev_chunk[d][i], cudaEventDisableTiming));
+    for (int d = 0; d < 2; ++d) CU(cudaEventCreateWithFlags(&ctx->ev_io_free[d], cudaEventDisableTiming));
     int rc = upload_field(ctx.get(), GSN_FIELD_MNT4753_FR);
     if (rc) return rc;
     *out = ctx.release();
@@ -389,6 +392,7 @@ int gsn_ctx_destroy(gsn_ctx *ctx) {
     ctx->plans32.clear();
     for (int d = 0; d < 2; ++d)
         for (int i = 0; i < 16; ++i) if (ctx->ev_chunk[d][i]) cudaEventDestroy(ctx->ev_chunk[d][i]);
+    for (int d = 0; d < 2; ++d) if (ctx->ev_io_free[d]) cudaEventDestroy(ctx->ev_io_free[d]);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -407,6 +411,7 @@ int gsn_ctx_trim(gsn_ctx *ctx) {
     ctx->plans32.clear();
     if (ctx->work.p) { cudaFree(ctx->work.p); ctx->work.p = nullptr; ctx->work.bytes = 0; }
     if (ctx->io.p) { cudaFree(ctx->io.p); ctx->io.p = nullptr; ctx->io.bytes = 0; }
+    if (ctx->io2.p) { cudaFree(ctx->io2.p); ctx->io2.p = nullptr; ctx->io2.bytes = 0; }
     return GSN_OK;
 }
 
@@ -461,29 +466,31 @@ int gsn_ntt768_device(gsn_ctx *ctx, uint32_t *d_limbs, size_t n, size_t batch, c
     return gsn_ntt768_strided_device(ctx, d_limbs, n, batch, 0, omega, inverse, stream);
 }
 
-int gsn_ntt768_host(gsn_ctx *ctx, uint32_t *limbs, size_t n, const uint32_t *omega, int inverse) {
-    if (!ctx || !limbs || !omega) return fail(GSN_ERR_INVALID_ARG, "null argument");
-    int rc = check_n(n, 1);
-    if (rc) return rc;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    CU(cudaSetDevice(ctx->device));
-    Plan768 *pl;
-    if ((rc = get_plan768(ctx, ilog2(n), omega, inverse, inverse, &pl))) return rc;
-    if ((rc = ensure_io(ctx, n * 96))) return rc;
-    uint32_t *io = (uint32_t *)ctx->io.p;
+// Enqueue one host-pointer transform on the context's three streams (copy-in, compute, copy-out) without
+// waiting for it: H2D in column blocks, pass 1 per block as it lands, middle passes, last pass per block of
+// output columns, D2H per block.  `io` is the device staging buffer to use; ev_free (may be null) is
+// recorded on the copy-out stream when the last D2H of this transform has been issued.
+static int enqueue_ntt768_host(gsn_ctx *ctx, Plan768 *pl, uint32_t *limbs, size_t n, uint32_t *io, cudaEvent_t wait_before_h2d,
+                               cudaEvent_t ev_free, bool first) {
+    int rc;
     const size_t P = pl->digits.size();
     cudaStream_t st = ctx->stream;
-    if (P < 2 || n * 96 < (8u << 20)) {  // small: copy in, transform, copy out
+    if (wait_before_h2d) {
+        CU(cudaStreamWaitEvent(ctx->s_in, wait_before_h2d, 0));
+        CU(cudaStreamWaitEvent(st, wait_before_h2d, 0));
+    }
+    if (P < 2 || n * 96 < (8u << 20)) {  // small: copy in, transform, copy out on the compute stream
         CU(cudaMemcpyAsync(io, limbs, n * 96, cudaMemcpyHostToDevice, st));
         if ((rc = launch_ntt768(ctx, pl, io, 1, 0, nullptr, st))) return rc;
         CU(cudaMemcpyAsync(limbs, io, n * 96, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+        if (ev_free) {
+            CU(cudaEventRecord(ev_free, st));
+        }
         return GSN_OK;
     }
-    // Pipelined: the first pass works on columns of the (2^l_1 x n/2^l_1) view of the input, so the
-    // H2D copy is cut into column blocks (2-D copies) and each block's tiles start as soon as it has
-    // landed; the last pass produces column blocks of the (n/2^l_1 x 2^l_1) view of the output, which
-    // are copied back while later blocks are still being computed.
+    // The first pass works on columns of the (2^l_1 x n/2^l_1) view of the input, so the H2D copy is cut into
+    // column blocks (2-D copies) and each block's tiles start as soon as it has landed; the last pass produces
+    // column blocks of the (n/2^l_1 x 2^l_1) view of the output, copied back while later blocks are computed.
     const uint32_t l1 = pl->digits[0], lP = pl->digits[P - 1];
     const uint64_t cols_in = n >> l1, rows_in = 1ull << l1;     // input view: rows_in x cols_in
     const uint64_t cols_out = 1ull << l1, rows_out = n >> l1;   // output view: rows_out x cols_out (k1 fastest)
@@ -492,8 +499,11 @@ int gsn_ntt768_host(gsn_ctx *ctx, uint32_t *limbs, size_t n, const uint32_t *ome
     while (chunks > 1 && (cols_in % chunks || cols_out % chunks || tiles % chunks || (cols_in / chunks) * rows_in < 1024 ||
                           (cols_out / chunks) * (1ull << lP) < 1024)) chunks >>= 1;
     if ((rc = ensure_work(ctx, n * 96))) return rc;
-    CU(cudaEventRecord(ctx->ev0, st));                 // order the copy streams after earlier work on the context
-    CU(cudaStreamWaitEvent(ctx->s_in, ctx->ev0, 0));
+    if (first) {  // order the copy-in stream after earlier (asynchronous, device-pointer) work on the context; later
+                  // transforms of a batch must NOT wait for the compute stream, or their H2D could not overlap it
+        CU(cudaEventRecord(ctx->ev0, st));
+        CU(cudaStreamWaitEvent(ctx->s_in, ctx->ev0, 0));
+    }
     const uint64_t cw_in = cols_in / chunks, cw_out = cols_out / chunks, tiles_per_chunk = tiles / chunks;
     for (int c = 0; c < chunks; ++c) {
         CU(cudaMemcpy2DAsync(io + c * cw_in * 24, cols_in * 96, limbs + c * cw_in * 24, cols_in * 96, cw_in * 96, rows_in, cudaMemcpyHostToDevice, ctx->s_in));
@@ -511,9 +521,50 @@ int gsn_ntt768_host(gsn_ctx *ctx, uint32_t *limbs, size_t n, const uint32_t *ome
         CU(cudaStreamWaitEvent(ctx->s_out, ctx->ev_chunk[1][c], 0));
         CU(cudaMemcpy2DAsync(limbs + c * cw_out * 24, cols_out * 96, io + c * cw_out * 24, cols_out * 96, cw_out * 96, rows_out, cudaMemcpyDeviceToHost, ctx->s_out));
     }
-    CU(cudaStreamSynchronize(ctx->s_out));
-    CU(cudaStreamSynchronize(st));
+    if (ev_free) {
+        CU(cudaEventRecord(ev_free, ctx->s_out));
+    }
     return GSN_OK;
+}
+
+int gsn_ntt768_host_batch(gsn_ctx *ctx, uint32_t *const *limbs, size_t count, size_t n, const uint32_t *omega, int inverse) {
+    if (!ctx || !limbs || !omega) return fail(GSN_ERR_INVALID_ARG, "null argument");
+    for (size_t i = 0; i < count; ++i)
+        if (!limbs[i]) return fail(GSN_ERR_INVALID_ARG, "limbs[%zu] is null", i);
+    int rc = check_n(n, 1);
+    if (rc) return rc;
+    if (count == 0) return GSN_OK;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    Plan768 *pl;
+    if ((rc = get_plan768(ctx, ilog2(n), omega, inverse, inverse, &pl))) return rc;
+    if ((rc = ensure_io(ctx, n * 96))) return rc;
+    if (count > 1) {
+        if (ctx->io2.bytes < n * 96) {
+            if (ctx->io2.p) { cudaFree(ctx->io2.p); ctx->io2.p = nullptr; ctx->io2.bytes = 0; }
+            if ((rc = dev_alloc(ctx->io2, n * 96))) return rc;
+        }
+    }
+    // Transform i uses staging buffer i % 2; its copy-in waits until the copy-out of transform i - 2 is done.
+    // The three streams are in order, so H2D of i+1 overlaps the passes and the D2H of i (full-duplex PCIe).
+    for (size_t i = 0; i < count; ++i) {
+        uint32_t *io = (uint32_t *)((i & 1) ? ctx->io2.p : ctx->io.p);
+        if ((rc = enqueue_ntt768_host(ctx, pl, limbs[i], n, io, i >= 2 ? ctx->ev_io_free[i & 1] : nullptr, ctx->ev_io_free[i & 1], i == 0))) {
+            cudaStreamSynchronize(ctx->s_out);
+            cudaStreamSynchronize(ctx->stream);
+            return rc;
+        }
+    }
+    CU(cudaStreamSynchronize(ctx->s_out));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->s_in));
+    return GSN_OK;
+}
+
+int gsn_ntt768_host(gsn_ctx *ctx, uint32_t *limbs, size_t n, const uint32_t *omega, int inverse) {
+    uint32_t *one[1] = {limbs};
+    if (!limbs) return fail(GSN_ERR_INVALID_ARG, "null argument");
+    return gsn_ntt768_host_batch(ctx, one, 1, n, omega, inverse);
 }
 
 int gsn_ntt768_time_device(gsn_ctx *ctx, uint32_t *d_limbs, size_t n, size_t batch, const uint32_t *omega, int inverse, int reps,

@@ -101,6 +101,16 @@ class Context:
         self._check(self.L.gsn_ntt768_host(self._h, _ptr(a), a.shape[0], _ptr(omega), int(bool(inverse))))
         return a
 
+    def best_fft768_batch(self, arrays, omega, inverse=False):
+        """in-place transforms of several host (n, 24) uint32 arrays with overlapped copies (gsn_ntt768_host_batch)"""
+        n = arrays[0].shape[0]
+        for a in arrays:
+            assert a.dtype == np.uint32 and a.flags["C_CONTIGUOUS"] and a.shape == (n, NL)
+        omega = _limbs(omega)
+        ptrs = (C.c_void_p * len(arrays))(*[a.ctypes.data for a in arrays])
+        self._check(self.L.gsn_ntt768_host_batch(self._h, ptrs, len(arrays), n, _ptr(omega), int(bool(inverse))))
+        return arrays
+
     def ntt768(self, a, omega, inverse=False):
         out = np.ascontiguousarray(a, dtype=np.uint32).reshape(-1, NL).copy()
         return self.best_fft768(out, omega, inverse)

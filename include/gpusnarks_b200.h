@@ -69,6 +69,12 @@ int gsn_launch_count(gsn_ctx *ctx, uint64_t *count);
  * host variant: `limbs` is host memory (n * 24 words), copied H2D, transformed, copied back
  * (blocking, like the reference's two cudaMemcpy, fft_kernel.cu:131,144). */
 int gsn_ntt768_host(gsn_ctx *ctx, uint32_t *limbs, size_t n, const uint32_t omega[GSN_FP768_LIMBS], int inverse);
+/* `count` independent host vectors of n elements each, transformed in place.  Same result as `count`
+ * calls of gsn_ntt768_host, but the copy-in of vector i+1 overlaps the passes and the copy-out of vector i
+ * (two staging buffers, three streams), so a sequence of transforms runs at PCIe speed in both
+ * directions at once -- what a prover's back-to-back FFTs want.  Blocking. */
+int gsn_ntt768_host_batch(gsn_ctx *ctx, uint32_t *const *limbs, size_t count, size_t n, const uint32_t omega[GSN_FP768_LIMBS],
+                          int inverse);
 /* device variant: `d_limbs` is device memory holding `batch` consecutive transforms of n
  * elements; stream-ordered on `stream` (a cudaStream_t, NULL = the context's stream);
  * returns after enqueueing. */

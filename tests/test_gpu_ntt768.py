@@ -83,6 +83,22 @@ def test_batched_and_strided_device(ctx):
         assert (got.reshape(exp.shape) == exp).all(), (logn, batch, log_r)
 
 
+@pytest.mark.parametrize("logn,count", [(6, 5), (12, 3), (18, 4), (20, 3)])
+def test_host_batch_matches_single_calls(ctx, logn, count):
+    """gsn_ntt768_host_batch (overlapped copies, two staging buffers) == one gsn_ntt768_host call per vector"""
+    n = 1 << logn
+    w = fieldgen.omega768(n)
+    vecs = [fieldgen.random_elements(n, 1000 + 10 * logn + i) for i in range(count)]
+    exp = [ctx.ntt768(v, w) for v in vecs]
+    got = [v.copy() for v in vecs]
+    ctx.best_fft768_batch(got, w)
+    for g_, e in zip(got, exp):
+        assert (g_ == e).all()
+    ctx.best_fft768_batch(got, w, inverse=True)
+    for g_, v in zip(got, vecs):
+        assert (g_ == v).all()
+
+
 def test_fq_field(ctx):
     """the reference's literal modulus (MNT4-753 Fq, 2-adicity 15)"""
     import gpusnarks_b200 as g
