@@ -67,3 +67,18 @@ def test_two_rank_fourstep_nccl():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "FOURSTEP_OK" in out.stdout
+
+
+def test_cpp_drop_in_driver_runs():
+    """the reference-shaped C++ driver (tests/cpp/test_fft_main.cpp = reference test/main.cpp:34-87 with a real
+    omega and the corrected host FFT): best_fft<fields::Scalar> / best_fft<dummy_fields::Field> through the
+    header shim and the C ABI, device result == host FFT"""
+    exe = os.path.join(ROOT, "tests", "cpp", "test_fft_main")
+    if not os.path.exists(exe):
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.check_call([cxx, "-O2", "-fopenmp", "-std=c++17", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle"),
+                               "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_fft_main.cpp"), "-L" + os.path.join(ROOT, "gpusnarks_b200"),
+                               "-lgpusnarks_b200", "-Wl,-rpath," + os.path.join(ROOT, "gpusnarks_b200")])
+    out = subprocess.run([exe, "16", "20"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("DONE") == 2 and "MISMATCH" not in out.stdout and "Missmatch" not in out.stdout
