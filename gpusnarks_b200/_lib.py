@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgpusnarks_b200.so")
+LIB_PATH = os.environ.get("GSN_LIB") or os.path.join(HERE, "libgpusnarks_b200.so")  # GSN_LIB: experiment builds
 
 # every symbol include/gpusnarks_b200.h declares (tests check that the .so exports them all)
 SYMBOLS = [

@@ -170,10 +170,10 @@ ntt768_pass(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, const 
     // ---- ph = 0: pre-twiddle (one product per element); ph = s >= 1: butterfly stage s
     for (uint32_t ph = g.has_pre ? 0u : 1u; ph <= lq; ++ph) {
         const uint32_t work = ph == 0 ? T : (T >> 1);
-        for (uint32_t b = threadIdx.x; b < work; b += THREADS) {
-            uint32_t lo = 0, hi;
-            const uint32_t *wp;
-            bool unit = false;  // twiddle == 1: no product (warp uniform by construction)
+        // work item b -> (lo, hi, twiddle pointer, unit flag)
+        auto locate = [&](uint32_t b, uint32_t &lo, uint32_t &hi, const uint32_t *&wp, bool &unit) {
+            lo = 0;
+            unit = false;  // twiddle == 1: no product (warp uniform by construction)
             if (ph == 0) {
                 hi = b;
                 const uint32_t slot = b >> lq;
@@ -198,6 +198,12 @@ ntt768_pass(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, const 
                 hi = lo + m;
                 wp = wloc + (size_t)((jj << (lq - ph)) << g.wloc_shift) * NL;
             }
+        };
+        for (uint32_t b = threadIdx.x; b < work; b += THREADS) {
+            uint32_t lo, hi;
+            const uint32_t *wp;
+            bool unit;
+            locate(b, lo, hi, wp, unit);
             uint4 *sh = tile + slot_of(hi) * SMEM_PITCH4;
             uint32_t t[NL];
             if (unit) {
