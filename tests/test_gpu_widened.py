@@ -79,3 +79,12 @@ def test_coset_transform_roundtrip_and_definition(ctx, logn):
     pw = pyref.ints_to_array([pyref.mont(pow(shift_int, i, p)) for i in range(n)])
     assert (ev == O.fft768(O.fp768_binop("mul", a, pw), w, -1)).all()
     assert (ctx.coset_ntt768(ev, w, shift, inverse=True) == a).all()
+
+
+def test_c_abi_from_plain_c_on_device(tmp_path):
+    """tests/c/capi_smoke.c (C99) against the library on the GPU: an 8-point 32-bit transform equals the DFT definition"""
+    import test_host_cpp
+    import subprocess
+    exe = test_host_cpp._build_c_smoke(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "capi ok (device)" in out.stdout, out.stdout + out.stderr

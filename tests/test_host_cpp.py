@@ -40,3 +40,21 @@ def test_reference_main_cpp_compiles_unmodified(tmp_path):
                            ref, "-L" + os.path.join(ROOT, "gpusnarks_b200"), "-lgpusnarks_b200",
                            "-Wl,-rpath," + os.path.join(ROOT, "gpusnarks_b200"), "-o", exe])
     assert os.path.exists(exe)
+
+
+def _build_c_smoke(tmp_path):
+    from gpusnarks_b200 import build
+    build.build()
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    exe = str(tmp_path / "capi_smoke")
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(ROOT, "tests", "c", "capi_smoke.c"), "-L" + os.path.join(ROOT, "gpusnarks_b200"), "-lgpusnarks_b200",
+                           "-Wl,-rpath," + os.path.join(ROOT, "gpusnarks_b200")])
+    return exe
+
+
+def test_c_abi_from_plain_c(tmp_path):
+    """include/gpusnarks_b200.h is valid C99 and the library links from C; without a GPU the context refuses to exist"""
+    exe = _build_c_smoke(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "capi ok" in out.stdout, out.stdout + out.stderr
