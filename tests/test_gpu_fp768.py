@@ -47,3 +47,18 @@ def test_kats_from_reference_unit_test(ctx):
     assert pyref.array_to_ints(back) == [1522756]
     # a + b == p reduces to 0 (the reference leaves p, device_field_operators.h:193)
     assert pyref.array_to_ints(ctx.fp768_binop("add", one(p - 5), one(5))) == [0]
+
+
+def test_reference_shaped_cpp_unit_test(tmp_path):
+    """tests/cpp/device_field_operator_test.cpp: the reference's arithmetic unit test (KATs + fuzz) with the GMP judge
+    replaced by this repo's host field type and the mismatch assert switched on; subject = device code via the C ABI"""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    exe = str(tmp_path / "device_field_operator_test")
+    subprocess.check_call([cxx, "-O2", "-std=c++17", "-I" + os.path.join(root, "include"), "-o", exe,
+                           os.path.join(root, "tests", "cpp", "device_field_operator_test.cpp"), "-L" + os.path.join(root, "gpusnarks_b200"),
+                           "-lgpusnarks_b200", "-Wl,-rpath," + os.path.join(root, "gpusnarks_b200")])
+    out = subprocess.run([exe, "20000"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "device field operators ok" in out.stdout, out.stdout + out.stderr

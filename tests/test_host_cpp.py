@@ -58,3 +58,14 @@ def test_c_abi_from_plain_c(tmp_path):
     exe = _build_c_smoke(tmp_path)
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "capi ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_device_field_operator_test_compiles(tmp_path):
+    """the reference-shaped C++ arithmetic unit test builds against the headers and the C ABI (it runs under -m gpu)"""
+    from gpusnarks_b200 import build
+    build.build()
+    exe = str(tmp_path / "dfot")
+    subprocess.check_call([CXX, "-O2", "-std=c++17", "-Wall", "-I" + os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(ROOT, "tests", "cpp", "device_field_operator_test.cpp"), "-L" + os.path.join(ROOT, "gpusnarks_b200"),
+                           "-lgpusnarks_b200", "-Wl,-rpath," + os.path.join(ROOT, "gpusnarks_b200")])
+    assert os.path.exists(exe)
