@@ -267,14 +267,22 @@ int get_plan768(gsn_ctx *ctx, uint32_t logn, const uint32_t *omega, int inverse,
     return GSN_OK;
 }
 
+// Tile size of the 768-bit pass kernel for `total` elements: 2^10 (or the 2-adic valuation of total if smaller), but
+// small transforms prefer more, smaller tiles (never below the longest digit) until the grid covers every CTA slot
+// of the device -- 2^16 is 64 tiles of 1024 but 256 tiles of 256.
+uint32_t choose_log_tile768(const gsn_ctx *ctx, const Plan768 *pl, uint64_t total) {
+    uint32_t log_tile = 0;
+    while (log_tile < 10 && !((total >> log_tile) & 1)) ++log_tile;
+    while (log_tile > pl->lmax && (total >> log_tile) < 2ull * (uint64_t)ctx->sm_count) --log_tile;
+    return log_tile;
+}
+
 // Launches passes [q_begin, q_end) of the plan; tile range [tile0, tile0 + ntiles) of each (ntiles == 0: all).
 int launch_ntt768_range(gsn_ctx *ctx, Plan768 *pl, uint32_t *d_data, size_t batch, uint32_t log_r, const uint32_t *ext_pre, cudaStream_t st,
                         size_t q_begin, size_t q_end, uint64_t tile0, uint64_t ntiles, const gsn::ScatterDesc *scatter = nullptr) {
     const size_t P = pl->digits.size();
     const uint64_t total = (uint64_t)batch << (pl->logn + log_r);
-    uint32_t v2 = 0;
-    while (v2 < 10 && !((total >> v2) & 1)) ++v2;
-    const uint32_t log_tile = v2;  // min(10, 2-adic valuation of total) >= every digit
+    const uint32_t log_tile = choose_log_tile768(ctx, pl, total);
     int rc;
     if (P > 1 && (rc = ensure_work(ctx, total * 96))) return rc;
     uint32_t *work = (uint32_t *)ctx->work.p;
@@ -494,7 +502,7 @@ static int enqueue_ntt768_host(gsn_ctx *ctx, Plan768 *pl, uint32_t *limbs, size_
     const uint32_t l1 = pl->digits[0], lP = pl->digits[P - 1];
     const uint64_t cols_in = n >> l1, rows_in = 1ull << l1;     // input view: rows_in x cols_in
     const uint64_t cols_out = 1ull << l1, rows_out = n >> l1;   // output view: rows_out x cols_out (k1 fastest)
-    const uint64_t tiles = n >> 10;
+    const uint64_t tiles = n >> choose_log_tile768(ctx, pl, n);
     int chunks = 8;
     while (chunks > 1 && (cols_in % chunks || cols_out % chunks || tiles % chunks || (cols_in / chunks) * rows_in < 1024 ||
                           (cols_out / chunks) * (1ull << lP) < 1024)) chunks >>= 1;
@@ -509,7 +517,7 @@ static int enqueue_ntt768_host(gsn_ctx *ctx, Plan768 *pl, uint32_t *limbs, size_
         CU(cudaMemcpy2DAsync(io + c * cw_in * 24, cols_in * 96, limbs + c * cw_in * 24, cols_in * 96, cw_in * 96, rows_in, cudaMemcpyHostToDevice, ctx->s_in));
         CU(cudaEventRecord(ctx->ev_chunk[0][c], ctx->s_in));
         CU(cudaStreamWaitEvent(st, ctx->ev_chunk[0][c], 0));
-        // pass 1 tiles of this column block: tile t covers sub-transforms (= columns) [t * 2^(10-l1), ...)
+        // pass 1 tiles of this column block: tile t covers sub-transforms (= columns) [t * 2^(log_tile-l1), ...)
         if ((rc = launch_ntt768_range(ctx, pl, io, 1, 0, nullptr, st, 0, 1, c * tiles_per_chunk, tiles_per_chunk))) return rc;
     }
     if (P > 2 && (rc = launch_ntt768_range(ctx, pl, io, 1, 0, nullptr, st, 1, P - 1, 0, 0))) return rc;
