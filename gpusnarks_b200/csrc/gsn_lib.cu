@@ -22,6 +22,7 @@
 #include "../../include/gpusnarks_b200.h"
 #include "../../include/gsn_constants.h"
 #include "fp768.cuh"
+#include "g1.cuh"
 #include "../../include/fields/fp768_host.h"
 #include "microbench.cuh"
 #include "ntt32.cuh"
@@ -652,6 +653,49 @@ int gsn_fp768_inner_product_host(gsn_ctx *ctx, uint32_t *out, const uint32_t *a,
     if ((rc = gsn_fp768_inner_product_device(ctx, (uint32_t *)dc.p, (const uint32_t *)da.p, (const uint32_t *)db.p, count, nullptr))) return rc;
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaMemcpyAsync(out, dc.p, 96, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GSN_OK;
+}
+
+int gsn_g1_multiexp_device(gsn_ctx *ctx, uint32_t *d_out, const uint32_t *d_points, const uint32_t *d_scalars, size_t n, void *stream) {
+    if (!ctx || !d_out || !d_points || !d_scalars) return fail(GSN_ERR_INVALID_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->field != GSN_FIELD_MNT4753_FQ)
+        return fail(GSN_ERR_INVALID_ARG, "G1 arithmetic lives over MNT4-753 Fq: call gsn_set_field768(ctx, GSN_FIELD_MNT4753_FQ) first");
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    int rc;
+    if ((rc = ensure_work(ctx, std::max<size_t>(n, 1) * 288))) return rc;
+    constexpr int RT = 128;
+    auto red = gsn::g1_reduce_kernel<RT>;
+    if (!ctx->smem_configured.count((const void *)red)) {
+        CU(cudaFuncSetAttribute(red, cudaFuncAttributeMaxDynamicSharedMemorySize, RT * 288));
+        ctx->smem_configured.insert((const void *)red);
+    }
+    if (n) {
+        gsn::g1_scalar_mul_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((uint32_t *)ctx->work.p, d_points, d_scalars, n);
+        ctx->launches++;
+    }
+    red<<<1, RT, RT * 288, st>>>(d_out, (const uint32_t *)ctx->work.p, n);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return GSN_OK;
+}
+
+int gsn_g1_multiexp_host(gsn_ctx *ctx, uint32_t *out, const uint32_t *points, const uint32_t *scalars, size_t n) {
+    if (!ctx || !out || !points || !scalars) return fail(GSN_ERR_INVALID_ARG, "null argument");
+    DevBuf dp, ds, dout;
+    int rc;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        CU(cudaSetDevice(ctx->device));
+        if ((rc = dev_alloc(dp, std::max<size_t>(n, 1) * 288)) || (rc = dev_alloc(ds, std::max<size_t>(n, 1) * 96)) || (rc = dev_alloc(dout, 288))) return rc;
+        CU(cudaMemcpyAsync(dp.p, points, n * 288, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ds.p, scalars, n * 96, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if ((rc = gsn_g1_multiexp_device(ctx, (uint32_t *)dout.p, (const uint32_t *)dp.p, (const uint32_t *)ds.p, n, nullptr))) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaMemcpyAsync(out, dout.p, 288, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return GSN_OK;
 }

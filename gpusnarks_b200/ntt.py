@@ -194,6 +194,16 @@ class Context:
         self._check(self.L.gsn_fp768_inner_product_host(self._h, _ptr(out), _ptr(a), _ptr(b), a.shape[0]))
         return out
 
+    def g1_multiexp(self, points, scalars):
+        """sum_i scalars[i] * points[i] on MNT4-753 G1 -- the reference's multiexp<mnt4753_G1, Scalar>.  points: (n, 3, 24)
+        projective Montgomery limbs over Fq; scalars: (n, 24) raw integers.  The context field must be FIELD_FQ."""
+        points = np.ascontiguousarray(points, dtype=np.uint32).reshape(-1, 3, NL)
+        scalars = np.ascontiguousarray(scalars, dtype=np.uint32).reshape(-1, NL)
+        assert points.shape[0] == scalars.shape[0]
+        out = np.empty((3, NL), dtype=np.uint32)
+        self._check(self.L.gsn_g1_multiexp_host(self._h, _ptr(out), _ptr(points), _ptr(scalars), points.shape[0]))
+        return out
+
     def coset_ntt768(self, a, omega, shift, inverse=False):
         """forward: evaluations of the polynomial with coefficients a on the coset shift * <omega>;
         inverse: coefficients from such evaluations.  Host arrays in/out (device-resident inside)."""

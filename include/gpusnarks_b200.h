@@ -144,6 +144,16 @@ int gsn_fp768_powers_device(gsn_ctx *ctx, uint32_t *d_table, size_t count, const
 int gsn_fp768_inner_product_device(gsn_ctx *ctx, uint32_t *d_out, const uint32_t *d_a, const uint32_t *d_b, size_t count, void *stream);
 int gsn_fp768_inner_product_host(gsn_ctx *ctx, uint32_t out[GSN_FP768_LIMBS], const uint32_t *a, const uint32_t *b, size_t count);
 
+/* ---- MNT4-753 G1 multi-exponentiation sum_i s_i * P_i: the reference's multiexp<mnt4753_G1, Scalar>
+ * (reference cuda/multi_exp.h:24-25, cuda/multi_exp.cu:104-142; group law cuda/device_field.h:296-437).
+ * The context's 768-bit field must be GSN_FIELD_MNT4753_FQ (the curve's base field).  Points are
+ * homogeneous projective (X, Y, Z), 3 x 24 limbs each, Montgomery form, identity = any point with Z = 0;
+ * scalars are raw 768-bit little-endian integers (the reference reads their bits with hasBitAt).  The result
+ * is projective with canonical coordinates.  Algorithm as in the reference: one double-and-add per point,
+ * then a tree reduction (not a bucket method). */
+int gsn_g1_multiexp_host(gsn_ctx *ctx, uint32_t out[72], const uint32_t *points, const uint32_t *scalars, size_t n);
+int gsn_g1_multiexp_device(gsn_ctx *ctx, uint32_t *d_out, const uint32_t *d_points, const uint32_t *d_scalars, size_t n, void *stream);
+
 /* ---- 32-bit NTT over Z/mod (mod an odd prime < 2^31 with n | mod-1).
  * Replaces best_fft for the reference's 32-bit field sketch (fields/dummy_field.h:24-62). */
 int gsn_ntt32_host(gsn_ctx *ctx, uint32_t *a, size_t n, uint32_t omega, uint32_t mod, int inverse);

@@ -1,0 +1,92 @@
+"""MNT4-753 G1 multi-exponentiation on the GPU (reference multiexp<mnt4753_G1, Scalar>)
+against the textbook affine group law in Python big-ints (tests/g1ref.py).  Results are compared as affine
+points, so the projective representative does not matter."""
+import random
+
+import numpy as np
+import pytest
+
+import g1ref
+import pyref
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def fq_ctx(ctx):
+    import gpusnarks_b200 as g
+    ctx.set_field768(g.FIELD_FQ)
+    yield ctx
+    ctx.set_field768(g.FIELD_FR)
+
+
+def _pack_points(pts):
+    arr = np.zeros((len(pts), 3, 24), dtype=np.uint32)
+    for i, P in enumerate(pts):
+        for c, v in enumerate(g1ref.to_projective_mont(P)):
+            arr[i, c] = pyref.to_limbs(v)
+    return arr
+
+
+def _affine(out):
+    return g1ref.from_projective_mont(*[pyref.from_limbs(out[c]) for c in range(3)])
+
+
+def test_requires_fq_field(ctx):
+    import gpusnarks_b200 as g
+    with pytest.raises(g.GsnError) as e:
+        ctx.g1_multiexp(np.zeros((1, 3, 24), np.uint32), np.zeros((1, 24), np.uint32))
+    assert e.value.code == 1 and "Fq" in str(e.value)
+
+
+def test_small_scalars_and_group_law_cases(fq_ctx):
+    rng = random.Random(11)
+    P, R = g1ref.random_point(rng), g1ref.random_point(rng)
+    negP = (P[0], (g1ref.Q - P[1]) % g1ref.Q)
+    cases = [
+        ([P], [0]), ([P], [1]), ([P], [2]), ([P], [3]), ([P], [0xFFFFFFFF]), ([P], [1 << 32]), ([P], [(1 << 64) + 5]),
+        ([P, R], [1, 1]), ([P, P], [1, 1]),               # doubling inside the reduction
+        ([P, negP], [1, 1]), ([P, negP], [7, 7]),         # inverse points: identity
+        ([None, P], [5, 9]), ([P, None, R], [2, 3, 4]),   # identity inputs
+        ([P, R, P, R], [1, 2, 3, 4]),
+    ]
+    for pts, ks in cases:
+        out = fq_ctx.g1_multiexp(_pack_points(pts), pyref.ints_to_array(ks))
+        assert _affine(out) == g1ref.multiexp(pts, ks), (pts, ks)
+    # projective inputs with Z != 1: scale (X, Y, Z) by a field element
+    lam = rng.randrange(1, g1ref.Q)
+    arr = _pack_points([P])
+    for c, v in enumerate(g1ref.to_projective_mont(P)):
+        arr[0, c] = pyref.to_limbs(v * lam % g1ref.Q)
+    assert _affine(fq_ctx.g1_multiexp(arr, pyref.ints_to_array([12345]))) == g1ref.mul(12345, P)
+
+
+@pytest.mark.parametrize("n,seed", [(1, 1), (5, 2), (40, 3), (129, 4)])
+def test_random_full_width_scalars(fq_ctx, n, seed):
+    rng = random.Random(seed)
+    pts = [g1ref.random_point(rng) for _ in range(n)]
+    ks = [rng.randrange(pyref.FR) for _ in range(n)]
+    out = fq_ctx.g1_multiexp(_pack_points(pts), pyref.ints_to_array(ks))
+    assert _affine(out) == g1ref.multiexp(pts, ks)
+    # canonical coordinates
+    for c in range(3):
+        assert pyref.from_limbs(out[c]) < g1ref.Q
+
+
+def test_reference_test_shape_linearity(fq_ctx):
+    """reference test/main.cpp:135-179 multiplies 2^16..2^20 copies of one point; here 2^12 points (several distinct),
+    checked by linearity: multiexp(P, s) + multiexp(P, t) == multiexp(P, s + t)"""
+    rng = random.Random(9)
+    base = [g1ref.random_point(rng) for _ in range(8)]
+    n = 1 << 12
+    pts = [base[i % 8] for i in range(n)]
+    P = _pack_points(base)[np.arange(n) % 8]
+    s = [rng.randrange(1 << 64) for _ in range(n)]
+    t = [rng.randrange(1 << 64) for _ in range(n)]
+    a = _affine(fq_ctx.g1_multiexp(P, pyref.ints_to_array(s)))
+    b = _affine(fq_ctx.g1_multiexp(P, pyref.ints_to_array(t)))
+    c = _affine(fq_ctx.g1_multiexp(P, pyref.ints_to_array([x + y for x, y in zip(s, t)])))
+    assert g1ref.add(a, b) == c
+    # and against the model, folding equal points first: sum_i s_i P_(i mod 8) = sum_j (sum of s over class j) P_j
+    folded = [sum(s[j::8]) for j in range(8)]
+    assert a == g1ref.multiexp(base, folded)
