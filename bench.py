@@ -197,7 +197,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", type=int, default=0, help="override the transform size (default 20 at N=1, 24 at N>1)")
-    ap.add_argument("--cpu-sample-log-n", type=int, default=18)
+    ap.add_argument("--cpu-sample-log-n", type=int, default=20, help="size of the CPU reference sample (2^20 = the whole N=1 workload, ~4 s on 16 cores)")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="N>1: fused = last column pass stores into peer memory over NVLink; nccl = all_to_all_single + repack")
     args = ap.parse_args()

@@ -14,6 +14,13 @@
 // With it serial == parallel == naive DFT  A[i] = sum_j a[j] * omega^(i*j), natural
 // order in, natural order out.  The inverse transform (absent from the reference, F8)
 // follows the libff convention: forward transform with omega^-1, then scale by n^-1.
+//
+// Pinning (tests/test_oracle_pins.py).  The reference holds no golden vectors for the FFT (its only check is
+// GPU == host on a constant input, test/main.cpp:80-84), so this restatement is pinned against the reference itself,
+// compiled here from /root/reference into oracle/_ref: the reference's own fft_host.h templates with the one butterfly
+// statement corrected by sed, instantiated over the oracle's field types, agree with these functions bit for bit
+// (serial and parallel entry points, both fields); the UNPATCHED templates are asserted NOT to be a DFT.  Plus the
+// DFT definition in Python big-ints and the naive O(n^2) DFT below.
 #pragma once
 #include <cstddef>
 #include <cstdint>
