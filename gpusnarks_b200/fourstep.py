@@ -53,7 +53,7 @@ class CudaBackend:
                                   pre_table=pre_table.data_ptr() if pre_table is not None else None, stream=self._stream())
 
     def table(self, rows, cols, row0, col0, n_total, omega, inverse_root=False, scale=False):
-        t = torch.empty((rows, cols, F.NL), dtype=torch.int32, device=self.device)
+        t = torch.empty((rows, cols, 2 * F.NL), dtype=torch.int32, device=self.device)  # (w, w'') per entry
         self.ctx.fourstep_table768(t.data_ptr(), rows, cols, row0, col0, n_total, omega, inverse_root=inverse_root, scale=scale,
                                    stream=self._stream())
         return t

@@ -185,6 +185,10 @@ class Context:
         self._check(self.L.gsn_fp768_powers_device(self._h, C.c_void_p(d_table), int(count), _ptr(base), _ptr(sc) if sc is not None else None,
                                                    C.c_void_p(stream or 0)))
 
+    def fp768_twiddle_table_device(self, d_table, d_elems, count, stream=None):
+        """count Montgomery-form elements (96 B each) -> pre-twiddle table of the transform kernels (192 B per entry)"""
+        self._check(self.L.gsn_fp768_twiddle_table_device(self._h, C.c_void_p(d_table), C.c_void_p(d_elems), int(count), C.c_void_p(stream or 0)))
+
     def multiexp768(self, a, b):
         """sum_i a[i] * b[i] -- the reference's multiexp<Scalar, Scalar> (cuda/multi_exp.h:24-25) on host arrays"""
         a = np.ascontiguousarray(a, dtype=np.uint32).reshape(-1, NL)
@@ -216,7 +220,13 @@ class Context:
             self.h2d(d, a)
             if not inverse:
                 self.fp768_powers_device(t, n, shift)
-                self.ntt768_device_ex(d, n, omega, pre_table=t)
+                t2 = self.device_alloc(2 * a.nbytes)
+                try:
+                    self.fp768_twiddle_table_device(t2, t, n)
+                    self.ntt768_device_ex(d, n, omega, pre_table=t2)
+                    self.synchronize()
+                finally:
+                    self.device_free(t2)
             else:
                 self.ntt768_device(d, n, omega, inverse=True)
                 self.fp768_powers_device(t, n, F.mont_inverse(shift))

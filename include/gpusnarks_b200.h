@@ -89,7 +89,7 @@ int gsn_ntt768_prepare(gsn_ctx *ctx, size_t n, size_t batch, const uint32_t omeg
 int gsn_ntt768_strided_device(gsn_ctx *ctx, uint32_t *d_limbs, size_t n, size_t batch, unsigned log_r,
                               const uint32_t omega[GSN_FP768_LIMBS], int inverse, void *stream);
 /* General form.  flags: GSN_FLAG_INVERSE_ROOT uses omega^-1 and (unless GSN_FLAG_NO_SCALE)
- * scales by n^-1.  d_pre_table (device, batch*n*2^log_r elements, may be NULL): every input
+ * scales by n^-1.  d_pre_table (device, batch*n*2^log_r entries of GSN_TWIDDLE_TABLE_WORDS words, may be NULL): every input
  * element is first multiplied by the table entry of the same index -- the four-step twiddles
  * produced by gsn_fourstep_table768, fused into the first pass of the transform. */
 #define GSN_FLAG_INVERSE_ROOT 1u
@@ -119,7 +119,7 @@ int gsn_peer_barrier(gsn_ctx *ctx, uint32_t *const *peer_flags, unsigned n_peers
 int gsn_ipc_export(gsn_ctx *ctx, void *dptr, unsigned char handle[64]);
 int gsn_ipc_import(gsn_ctx *ctx, const unsigned char handle[64], void **dptr);
 int gsn_ipc_close(gsn_ctx *ctx, void *dptr);
-/* d_table[r * cols + c] = omega^(+-(row0 + r) * (col0 + c))  [* n_total^-1 with GSN_FLAG_SCALE_TABLE],
+/* d_table (rows * cols entries of GSN_TWIDDLE_TABLE_WORDS words) <- omega^(+-(row0 + r) * (col0 + c))  [* n_total^-1 with GSN_FLAG_SCALE_TABLE],
  * r < rows, c < cols, omega a primitive n_total-th root (GSN_FLAG_INVERSE_ROOT: omega^-1):
  * the twiddles between the column and the row transforms of a four-step (Bailey) NTT for
  * the shard that owns rows row0.. and columns col0.. (reference structure: the omega_j /
@@ -139,6 +139,12 @@ int gsn_fp768_binop_device(gsn_ctx *ctx, int op, uint32_t *d_out, const uint32_t
  * inverse transform followed by gsn_fp768_binop_device(mul, powers(g^-1)). */
 int gsn_fp768_powers_device(gsn_ctx *ctx, uint32_t *d_table, size_t count, const uint32_t base[GSN_FP768_LIMBS],
                             const uint32_t *scale, void *stream);
+/* Pre-twiddle tables of gsn_ntt768_device_ex / _scatter are in the transform kernels' fixed-operand format:
+ * 48 words per entry, w (plain integer) followed by w'' = floor(w * 2^768 / p).  This converts `count` field
+ * elements (24 words each, Montgomery form, canonical) into such a table (count * 192 bytes).
+ * gsn_fourstep_table768 produces this format directly. */
+#define GSN_TWIDDLE_TABLE_WORDS 48
+int gsn_fp768_twiddle_table_device(gsn_ctx *ctx, uint32_t *d_table, const uint32_t *d_elems, size_t count, void *stream);
 /* sum_i a[i] * b[i] in the field (Montgomery products): the reference's multiexp<Scalar, Scalar>
  * (reference cuda/multi_exp.h:24-25, cuda/multi_exp.cu:104-137; CPU form test/multiexp.h:3-13). */
 int gsn_fp768_inner_product_device(gsn_ctx *ctx, uint32_t *d_out, const uint32_t *d_a, const uint32_t *d_b, size_t count, void *stream);
