@@ -156,6 +156,20 @@ def ncu_traffic_bytes(name):
         return None
 
 
+def executed_utilisation(logn, ms_step, p_mac):
+    """wide-multiply issue slots the single-GPU transform really executes (fixed-operand product: 876 IMAD.WIDE + 48 IMAD
+    = 900 wide-equivalents; per pass of l stages a tile runs l - 1.875 stages' worth of products -- stage 1 and the unit
+    butterflies of stages 2-4 are skipped -- plus one product per element at every pass boundary) / time / peak"""
+    n = 1 << logn
+    passes = max(1, -(-logn // 10))
+    base, extra = divmod(logn, passes)
+    digits = [base + (1 if i < extra else 0) for i in range(passes)]
+    products = sum((max(l - 1.875, 0)) * n / 2 for l in digits) + (passes - 1) * n
+    slots = products * 900.0
+    return {"products_per_transform": products, "wide_equiv_slots_per_product": 900, "slots_per_s": slots / (ms_step * 1e-3),
+            "frac_of_peak": slots / (ms_step * 1e-3) / p_mac}
+
+
 def bench_ntt32(ctx, hbm_peak_gbs, logn=22, batch=16, reps=12):
     """BASELINE.json configs[1]: 32-bit prime-field NTT 2^22 on one B200 (HBM-bound).  `batch` distinct
     16 MiB buffers (256 MiB > L2) are transformed per launch pair so that inputs come from HBM; the
@@ -384,6 +398,10 @@ def main():
             "achieved": achieved / 1e12, "peak": p_mac / 1e12, "unit": "T wide-MAC/s (32x32+64 IMAD.WIDE.U32)",
             "frac": achieved / p_mac,
             "algorithmic_macs_per_butterfly": MACS_PER_BUTTERFLY,
+            # frac can exceed 1: the 1176-MAC figure is the CIOS product of SURVEY.md 8d, while the kernel multiplies
+            # by table twiddles with a fixed-operand product of 876 wide + 48 low multiplies (= 900 wide-equivalent
+            # issue slots) and skips unit twiddles.  `executed` is the multiplier-pipe utilisation of what really runs.
+            "executed": executed_utilisation(logn, ms_step, p_mac) if world == 1 else None,
             "peak_source": "gsn_int32_issue_rates: max over the IMAD.WIDE.U32 probes (accumulate form with distinct / shared multiplicands, .X carry chains), 8 independent accumulators, measured in this process (SASS-verified loops)",
             "int32_issue_rates_per_s": rates["rates"],
             "launches_per_step": kernels_per_step,
