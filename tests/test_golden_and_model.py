@@ -80,3 +80,12 @@ def test_g1_reference_model_self_consistency():
     assert g1ref.mul(6, P) == g1ref.add(g1ref.mul(2, P), g1ref.mul(4, P))
     assert g1ref.multiexp([P, R], [3, 5]) == g1ref.add(g1ref.mul(3, P), g1ref.mul(5, R))
     assert g1ref.from_projective_mont(*g1ref.to_projective_mont(P)) == P
+
+
+@pytest.mark.parametrize("p", [pyref.FR, pyref.FQ])
+def test_device_product_models(p):
+    """tools/model_products.py: limb-for-limb Python models of the device's CIOS and fixed-operand products (carries and
+    truncation exactly as in the PTX) against big-int arithmetic, both moduli, edge and random operands"""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import model_products
+    assert model_products.self_check(p, cases=250, seed=3) <= 2
