@@ -23,6 +23,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    if not os.path.exists(LIB_PATH) and not os.environ.get("GSN_LIB"):
+        try:  # a fresh checkout: build in-tree once (nvcc, sm_100a); failure falls through to the loud error below
+            from . import build as _build
+            _build.build()
+        except Exception:
+            pass
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             f"{LIB_PATH} is missing: build it with `python -m gpusnarks_b200.build` "
