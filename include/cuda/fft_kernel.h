@@ -68,4 +68,17 @@ void best_ifft(std::vector<FieldT> &a, const FieldT &omg) {
     gsn::fft_dispatch<FieldT>::run(a, omg, 1);
 }
 
+// Several equally long vectors over the 768-bit field in one call: same results as calling best_fft on each, but the
+// host<->device copies of consecutive vectors overlap with each other and with the transforms (gsn_ntt768_host_batch).
+inline void best_fft_batch(std::vector<std::vector<fields::Scalar>> &vs, const fields::Scalar &omg, bool inverse = false) {
+    if (vs.empty()) return;
+    std::vector<uint32_t *> ptrs;
+    for (auto &v : vs) {
+        if (v.size() != vs[0].size()) throw std::runtime_error("best_fft_batch: vectors must have equal length");
+        ptrs.push_back(reinterpret_cast<uint32_t *>(v.data()));
+    }
+    gsn::check(gsn_ntt768_host_batch(gsn::default_ctx(), ptrs.data(), ptrs.size(), vs[0].size(), omg.im_rep, inverse ? 1 : 0),
+               "gsn_ntt768_host_batch");
+}
+
 #endif
