@@ -14,6 +14,11 @@ SYMBOLS = [
     "gsn_device_count", "gsn_host_alloc", "gsn_host_free", "gsn_device_alloc", "gsn_device_free",
     "gsn_memcpy_h2d", "gsn_memcpy_d2h", "gsn_ctx_synchronize", "gsn_int32_issue_rates",
     "gsn_ntt768_time_device", "gsn_ntt32_time_device",
+    "gsn_ctx_set_option", "gsn_ntt768_plan_info", "gsn_coset_ntt768_device", "gsn_coset_ntt768_host",
+    "gsn_fourstep_create", "gsn_fourstep_destroy", "gsn_fourstep_info", "gsn_fourstep_buffers", "gsn_fourstep_connect",
+    "gsn_fourstep_forward", "gsn_fourstep_inverse", "gsn_fourstep_phase_ms",
+    "gsn_multi_create", "gsn_multi_destroy", "gsn_multi_ntt768_host", "gsn_multi_device_buffers", "gsn_multi_ntt768_device",
+    "gsn_multi_synchronize",
 ]
 
 _lib = None
@@ -74,6 +79,26 @@ def load():
     L.gsn_int32_issue_rates.argtypes = [vp, C.POINTER(C.c_double), i, C.POINTER(i), C.POINTER(i), C.POINTER(i)]
     L.gsn_ntt768_time_device.argtypes = [vp, vp, sz, sz, u32p, i, i, C.POINTER(C.c_float)]
     L.gsn_ntt32_time_device.argtypes = [vp, vp, sz, sz, u32, u32, i, i, C.POINTER(C.c_float)]
+    u64 = C.c_uint64
+    pu = C.POINTER(C.c_uint)
+    L.gsn_ctx_set_option.argtypes = [vp, i, u64]
+    L.gsn_ntt768_plan_info.argtypes = [vp, sz, u32p, i, u64p, pu, pu, u64p, u64p]
+    L.gsn_coset_ntt768_device.argtypes = [vp, vp, sz, sz, u32p, u32p, i, vp]
+    L.gsn_coset_ntt768_host.argtypes = [vp, u32p, sz, u32p, u32p, i]
+    L.gsn_fourstep_create.argtypes = [vp, C.POINTER(vp), C.c_uint, u32p, C.c_uint, C.c_uint, C.c_uint]
+    L.gsn_fourstep_destroy.argtypes = [vp]
+    L.gsn_fourstep_info.argtypes = [vp, pu, pu, pu, u64p, pu]
+    L.gsn_fourstep_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.gsn_fourstep_connect.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.gsn_fourstep_forward.argtypes = [vp, vp, C.POINTER(vp)]
+    L.gsn_fourstep_inverse.argtypes = [vp, vp, C.POINTER(vp)]
+    L.gsn_fourstep_phase_ms.argtypes = [vp, C.POINTER(C.c_float), u64p]
+    L.gsn_multi_create.argtypes = [C.POINTER(vp), C.POINTER(i), C.c_uint, sz, u32p, C.c_uint]
+    L.gsn_multi_destroy.argtypes = [vp]
+    L.gsn_multi_ntt768_host.argtypes = [vp, u32p, i]
+    L.gsn_multi_device_buffers.argtypes = [vp, C.c_uint, C.POINTER(vp), C.POINTER(vp)]
+    L.gsn_multi_ntt768_device.argtypes = [vp, i]
+    L.gsn_multi_synchronize.argtypes = [vp]
     for s in SYMBOLS:
         if s != "gsn_last_error":
             getattr(L, s).restype = i

@@ -18,9 +18,10 @@
 // container 768, so there are 15 bits of headroom) and are made canonical, [0, p),
 // only where they leave the transform.
 //
-// The modulus lives in __constant__ memory so that one binary serves MNT4-753 Fr
-// (default) and Fq (the reference's literal `_mod`); with fully unrolled loops every
-// modulus word is a constant-bank operand of the IMAD and costs no register.
+// The modulus is a kernel parameter (FieldConstants768, `const __grid_constant__`), so one
+// binary serves MNT4-753 Fr (default) and Fq (the reference's literal `_mod`) per launch;
+// with fully unrolled loops every modulus word is a constant-bank operand of the IMAD and
+// costs no register.
 #pragma once
 #include <cstdint>
 
@@ -31,14 +32,19 @@ constexpr int NL = 24;  // reference: #define SIZE (768 / 32), cuda/device_field
 struct FieldConstants768 {
     uint32_t p[NL];    // modulus
     uint32_t p2[NL];   // 2 * modulus
+    uint32_t p3[NL];   // 3 * modulus (lazy subtraction: y = u + 3p - t for t in [0, 3p))
+    uint32_t p6[NL];   // 6 * modulus (the same for the unit-twiddle butterflies of stage 2, whose t is < 6p)
     uint32_t r1[NL];   // R mod p  (Montgomery one)
     uint32_t r2[NL];   // R^2 mod p
     uint32_t np0;      // -p^-1 mod 2^32
-    uint32_t pad[3];
+    uint32_t qmagic;   // floor(2^32 / ((p >> 736) + 1)): quotient estimate of reduce_small
+    uint32_t pad[2];
     uint32_t nprime[NL];  // -p^-1 mod 2^768 (builds the quotient constants of the fixed-operand product)
 };
-
-__constant__ FieldConstants768 c_fp;
+// The constants travel with every launch as a `const __grid_constant__` kernel parameter (param space is a constant
+// bank: with fully unrolled loops each modulus word is an immediate-offset constant operand of the IMAD, no register,
+// no upload, and -- unlike one __constant__ symbol per device -- nothing that a second context could overwrite).
+#define GSN_FC const FieldConstants768 &fc
 
 // ------------------------------------------------------------------ carry-chain primitives
 __device__ __forceinline__ uint32_t add_cc(uint32_t a, uint32_t b) {
@@ -91,7 +97,7 @@ __device__ __forceinline__ uint32_t sub_raw(uint32_t *r, const uint32_t *a, cons
     for (int i = 1; i < NL; ++i) r[i] = subc_cc(a[i], b[i]);
     return subc(0u, 0u);  // 0 - 0 - borrow
 }
-// if a >= m: a -= m      (m = c_fp.p or c_fp.p2), branch free
+// if a >= m: a -= m      (m = fc.p or fc.p2), branch free
 __device__ __forceinline__ void cond_sub(uint32_t *a, const uint32_t *m) {
     uint32_t d[NL];
     uint32_t borrow = sub_raw(d, a, m);
@@ -99,27 +105,27 @@ __device__ __forceinline__ void cond_sub(uint32_t *a, const uint32_t *m) {
     for (int i = 0; i < NL; ++i) a[i] = borrow ? a[i] : d[i];
 }
 // lazy butterfly outputs: inputs u, t in [0, 2p)  ->  x = u + t, y = u - t, both in [0, 2p)
-__device__ __forceinline__ void add_lazy(uint32_t *x, const uint32_t *u, const uint32_t *t) {
+__device__ __forceinline__ void add_lazy(GSN_FC, uint32_t *x, const uint32_t *u, const uint32_t *t) {
     add_raw(x, u, t);          // < 4p < 2^768
-    cond_sub(x, c_fp.p2);
+    cond_sub(x, fc.p2);
 }
-__device__ __forceinline__ void sub_lazy(uint32_t *y, const uint32_t *u, const uint32_t *t) {
+__device__ __forceinline__ void sub_lazy(GSN_FC, uint32_t *y, const uint32_t *u, const uint32_t *t) {
     uint32_t borrow = sub_raw(y, u, t);   // in (-2p, 2p)
     // y += borrow ? 2p : 0
-    y[0] = add_cc(y[0], c_fp.p2[0] & borrow);
+    y[0] = add_cc(y[0], fc.p2[0] & borrow);
 #pragma unroll
-    for (int i = 1; i < NL - 1; ++i) y[i] = addc_cc(y[i], c_fp.p2[i] & borrow);
-    y[NL - 1] = addc(y[NL - 1], c_fp.p2[NL - 1] & borrow);
+    for (int i = 1; i < NL - 1; ++i) y[i] = addc_cc(y[i], fc.p2[i] & borrow);
+    y[NL - 1] = addc(y[NL - 1], fc.p2[NL - 1] & borrow);
 }
 // [0, 2p) -> [0, p)
-__device__ __forceinline__ void canonicalize(uint32_t *a) { cond_sub(a, c_fp.p); }
+__device__ __forceinline__ void canonicalize(GSN_FC, uint32_t *a) { cond_sub(a, fc.p); }
 
 // ------------------------------------------------------------------ Montgomery product
 // One outer CIOS step for multiplier word `bi` (reference: one pass of the `i` loop of
 // ciosMontgomeryMultiply, device_field_operators.h:156-184).  `ev`/`od` are the accumulators
 // aligned to even/odd limbs of the frame on entry to this step (see file header).
 template <bool FIRST>
-__device__ __forceinline__ void cios_step(uint32_t *ev, uint32_t *od, const uint32_t *a, uint32_t bi) {
+__device__ __forceinline__ void cios_step(GSN_FC, uint32_t *ev, uint32_t *od, const uint32_t *a, uint32_t bi) {
     if (FIRST) {
 #pragma unroll
         for (int j = 0; j < NL; j += 2) mul_wide(od[j], od[j + 1], a[j + 1], bi);
@@ -138,13 +144,13 @@ __device__ __forceinline__ void cios_step(uint32_t *ev, uint32_t *od, const uint
         for (int j = 2; j < NL; j += 2) madc_wide_cc(ev[j], ev[j + 1], a[j], bi);
         od[NL - 1] = addc(od[NL - 1], 0u);
     }
-    const uint32_t m = ev[0] * c_fp.np0;
-    mad_wide_cc(od[0], od[1], c_fp.p[1], m);
+    const uint32_t m = ev[0] * fc.np0;
+    mad_wide_cc(od[0], od[1], fc.p[1], m);
 #pragma unroll
-    for (int j = 2; j < NL; j += 2) madc_wide_cc(od[j], od[j + 1], c_fp.p[j + 1], m);
-    mad_wide_cc(ev[0], ev[1], c_fp.p[0], m);
+    for (int j = 2; j < NL; j += 2) madc_wide_cc(od[j], od[j + 1], fc.p[j + 1], m);
+    mad_wide_cc(ev[0], ev[1], fc.p[0], m);
 #pragma unroll
-    for (int j = 2; j < NL; j += 2) madc_wide_cc(ev[j], ev[j + 1], c_fp.p[j], m);
+    for (int j = 2; j < NL; j += 2) madc_wide_cc(ev[j], ev[j + 1], fc.p[j], m);
     od[NL - 1] = addc(od[NL - 1], 0u);
     // ev[0] is now 0 mod 2^32: the frame shifts right one limb, ev <-> od swap roles.
 }
@@ -153,14 +159,14 @@ __device__ __forceinline__ void cios_step(uint32_t *ev, uint32_t *od, const uint
 // subtraction).  `B` is any callable  uint32_t B(int i)  giving word i of b, so the
 // multiplier can stream from shared memory without occupying 24 registers.
 template <typename BWord>
-__device__ __forceinline__ void mont_mul_lazy_w(uint32_t *r, const uint32_t *a, BWord b) {
+__device__ __forceinline__ void mont_mul_lazy_w(GSN_FC, uint32_t *r, const uint32_t *a, BWord b) {
     uint32_t ev[NL], od[NL];
-    cios_step<true>(ev, od, a, b(0));
-    cios_step<false>(od, ev, a, b(1));
+    cios_step<true>(fc, ev, od, a, b(0));
+    cios_step<false>(fc, od, ev, a, b(1));
 #pragma unroll
     for (int i = 2; i < NL; i += 2) {
-        cios_step<false>(ev, od, a, b(i));
-        cios_step<false>(od, ev, a, b(i + 1));
+        cios_step<false>(fc, ev, od, a, b(i));
+        cios_step<false>(fc, od, ev, a, b(i + 1));
     }
     // The last step ran with the roles exchanged (even accumulator = `od`) and left its
     // one-limb shift pending: value = (od >> 32) + ev.
@@ -175,13 +181,13 @@ struct RegWords {
     __device__ __forceinline__ uint32_t operator()(int i) const { return w[i]; }
 };
 
-__device__ __forceinline__ void mont_mul_lazy(uint32_t *r, const uint32_t *a, const uint32_t *b) {
-    mont_mul_lazy_w(r, a, RegWords{b});
+__device__ __forceinline__ void mont_mul_lazy(GSN_FC, uint32_t *r, const uint32_t *a, const uint32_t *b) {
+    mont_mul_lazy_w(fc, r, a, RegWords{b});
 }
 // canonical product, [0, p)
-__device__ __forceinline__ void mont_mul(uint32_t *r, const uint32_t *a, const uint32_t *b) {
-    mont_mul_lazy_w(r, a, RegWords{b});
-    canonicalize(r);
+__device__ __forceinline__ void mont_mul(GSN_FC, uint32_t *r, const uint32_t *a, const uint32_t *b) {
+    mont_mul_lazy_w(fc, r, a, RegWords{b});
+    canonicalize(fc, r);
 }
 
 // ------------------------------------------------------------------ fixed-operand ("Shoup") product
@@ -244,24 +250,27 @@ __device__ __forceinline__ void mul_lo768(uint32_t *r, const uint32_t *a, BWord 
     for (int i = 0; i < NL; ++i) row_mac<0, NL, NL - 1>(ev, od, a, b(i), i, 0, NL - i);
     merge_evod<NL>(r, ev, od);
 }
-struct ConstModulus { __device__ __forceinline__ uint32_t operator()(int i) const { return c_fp.p[i]; } };
-struct ConstNprime { __device__ __forceinline__ uint32_t operator()(int i) const { return c_fp.nprime[i]; } };
+struct ConstModulus { const FieldConstants768 &fc; __device__ __forceinline__ uint32_t operator()(int i) const { return fc.p[i]; } };
+struct ConstNprime { const FieldConstants768 &fc; __device__ __forceinline__ uint32_t operator()(int i) const { return fc.nprime[i]; } };
 
-// t = x * w mod p in [0, 2p).  x (< 2^768, any lazy value) is given word by word, twice (two passes over it);
-// tw points at a table entry: w[24] (plain, < p) followed by w''[24] = floor(w * 2^768 / p).
+// 96-byte table half -> registers (read-only path; table entries are 32-byte aligned)
+__device__ __forceinline__ void load_tw_half(uint32_t *r, const uint32_t *g) {
+    const uint4 *pw = reinterpret_cast<const uint4 *>(g);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        const uint4 v = __ldg(pw + c);
+        r[4 * c] = v.x; r[4 * c + 1] = v.y; r[4 * c + 2] = v.z; r[4 * c + 3] = v.w;
+    }
+}
+
+// t = x * w mod p, unreduced: t = x*w - q*p in [0, 3p) for ANY x < 2^768.  x is given word by word, twice (two passes
+// over it); w2 = w'' (registers: the caller may have prefetched it), tw points at the table entry whose first half
+// is w (plain, < p); it is fetched while the quotient product runs.
 template <typename XWords>
-__device__ __forceinline__ void shoup_mul_lazy(uint32_t *t, XWords x1, XWords x2, const uint32_t *tw) {
+__device__ __forceinline__ void shoup_mul_3p(GSN_FC, uint32_t *t, XWords x1, XWords x2, const uint32_t *w2, const uint32_t *tw) {
     uint32_t q[NL];
     {
-        uint32_t w2[NL], ev[NL + 4], od[NL + 4], hi[NL + 2];
-        {
-            const uint4 *pw = reinterpret_cast<const uint4 *>(tw + NL);
-#pragma unroll
-            for (int c = 0; c < 6; ++c) {
-                const uint4 v = __ldg(pw + c);
-                w2[4 * c] = v.x; w2[4 * c + 1] = v.y; w2[4 * c + 2] = v.z; w2[4 * c + 3] = v.w;
-            }
-        }
+        uint32_t ev[NL + 4], od[NL + 4], hi[NL + 2];
 #pragma unroll
         for (int k = 0; k < NL + 4; ++k) ev[k] = od[k] = 0;
 #pragma unroll
@@ -271,24 +280,62 @@ __device__ __forceinline__ void shoup_mul_lazy(uint32_t *t, XWords x1, XWords x2
         for (int k = 0; k < NL; ++k) q[k] = hi[k + 2];
     }
     uint32_t p3[NL];
-    mul_lo768(p3, q, ConstModulus{});
+    mul_lo768(p3, q, ConstModulus{fc});
     uint32_t p2v[NL];
     {
         uint32_t w[NL];
-        const uint4 *pw = reinterpret_cast<const uint4 *>(tw);
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-            const uint4 v = __ldg(pw + c);
-            w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
-        }
+        load_tw_half(w, tw);
         mul_lo768(p2v, w, x2);
     }
-    // t = x*w - q*p (mod 2^768), in [0, 3p): bring it into [0, 2p)
     t[0] = sub_cc(p2v[0], p3[0]);
 #pragma unroll
     for (int k = 1; k < NL - 1; ++k) t[k] = subc_cc(p2v[k], p3[k]);
     t[NL - 1] = subc(p2v[NL - 1], p3[NL - 1]);
-    cond_sub(t, c_fp.p2);
+}
+
+// t = x * w mod p in [0, 2p): the same with one conditional subtraction (strict callers)
+template <typename XWords>
+__device__ __forceinline__ void shoup_mul_lazy(GSN_FC, uint32_t *t, XWords x1, XWords x2, const uint32_t *tw) {
+    uint32_t w2[NL];
+    load_tw_half(w2, tw + NL);
+    shoup_mul_3p(fc, t, x1, x2, w2, tw);
+    cond_sub(t, fc.p2);
+}
+
+// ------------------------------------------------------------------ wide lazy ranges
+// Inside a pass nothing but the products reduces: a butterfly with t in [0, K p) maps u -> (u + t, u + K p - t).
+// K = 3 wherever t comes out of a product; the unit-twiddle butterflies take t as it is: stage 1 sees values below 3p
+// (canonical input, or the pre-twiddle product), the unit half of stage 2 values below 6p (K = 6).  Bounds: < 6p after
+// stage 1, < 12p after stage 2, + 3p per further stage = < 36p after a 10-stage pass (p < 2^753, container 2^768).  The
+// product accepts any x < 2^768, and values are brought back to [0, p) once, by reduce_small, where they leave the
+// transform.  That removes three carry-chain passes and two selects from every butterfly.
+// d = K p - t  (kp = fc.p3 or fc.p6)
+__device__ __forceinline__ void neg_wide(uint32_t *d, const uint32_t *kp, const uint32_t *t) {
+    d[0] = sub_cc(kp[0], t[0]);
+#pragma unroll
+    for (int i = 1; i < NL - 1; ++i) d[i] = subc_cc(kp[i], t[i]);
+    d[NL - 1] = subc(kp[NL - 1], t[NL - 1]);
+}
+// v < 1024p  ->  [0, p).  Quotient estimate from the top limb: with d = (p >> 736) + 1, q = floor(v[23] * floor(2^32/d) / 2^32)
+// satisfies floor(v/p) - 2 <= q <= floor(v/p) (tools/model_products.py checks the bound), so v - q*p is in [0, 3p).
+__device__ __forceinline__ void reduce_small(GSN_FC, uint32_t *v) {
+    const uint32_t q = __umulhi(v[NL - 1], fc.qmagic);
+    uint32_t qp[NL];
+    {
+        uint32_t lo, hi, carry = 0;
+#pragma unroll
+        for (int i = 0; i < NL; ++i) {  // q < 1024, p[i] < 2^32: q*p[i] + carry fits 64 bits
+            asm volatile("mad.lo.cc.u32 %0, %2, %3, %4; madc.hi.u32 %1, %2, %3, 0;" : "=r"(lo), "=r"(hi) : "r"(fc.p[i]), "r"(q), "r"(carry));
+            qp[i] = lo;
+            carry = hi;
+        }
+    }
+    v[0] = sub_cc(v[0], qp[0]);
+#pragma unroll
+    for (int i = 1; i < NL - 1; ++i) v[i] = subc_cc(v[i], qp[i]);
+    v[NL - 1] = subc(v[NL - 1], qp[NL - 1]);
+    cond_sub(v, fc.p2);
+    cond_sub(v, fc.p);
 }
 
 // ------------------------------------------------------------------ global memory access

@@ -15,9 +15,15 @@
 // The Montgomery product is ~1.2k instructions, and the group law calls it 25 times: it is kept out of line
 // (`fq_mul`, operands in local memory) so the kernels stay small enough for the instruction cache.
 #pragma once
+#include "../../include/gsn_constants.h"
 #include "fp768.cuh"
 
 namespace gsn {
+
+// The curve lives over MNT4-753 Fq whatever field the context's transforms use: its constants are a compile-time
+// __constant__ object (never written at run time), so G1 calls need no gsn_set_field768 and cannot race with it.
+__constant__ FieldConstants768 c_fq = {GSN_FQ_MOD, GSN_FQ_MOD2, GSN_FQ_MOD3, GSN_FQ_MOD6, GSN_FQ_R1, GSN_FQ_R2,
+                                       GSN_FQ_NP0, GSN_FQ_QMAGIC, {0, 0}, GSN_FQ_NPRIME768};
 
 struct G1 {
     uint32_t x[NL], y[NL], z[NL];
@@ -27,7 +33,7 @@ __device__ __noinline__ void fq_mul(uint32_t *r, const uint32_t *a, const uint32
     uint32_t x[NL], y[NL], t[NL];
 #pragma unroll
     for (int i = 0; i < NL; ++i) { x[i] = a[i]; y[i] = b[i]; }
-    mont_mul_lazy(t, x, y);
+    mont_mul_lazy(c_fq, t, x, y);
 #pragma unroll
     for (int i = 0; i < NL; ++i) r[i] = t[i];
 }
@@ -35,7 +41,7 @@ __device__ __noinline__ void fq_add(uint32_t *r, const uint32_t *a, const uint32
     uint32_t x[NL], y[NL], t[NL];
 #pragma unroll
     for (int i = 0; i < NL; ++i) { x[i] = a[i]; y[i] = b[i]; }
-    add_lazy(t, x, y);
+    add_lazy(c_fq, t, x, y);
 #pragma unroll
     for (int i = 0; i < NL; ++i) r[i] = t[i];
 }
@@ -43,21 +49,21 @@ __device__ __noinline__ void fq_sub(uint32_t *r, const uint32_t *a, const uint32
     uint32_t x[NL], y[NL], t[NL];
 #pragma unroll
     for (int i = 0; i < NL; ++i) { x[i] = a[i]; y[i] = b[i]; }
-    sub_lazy(t, x, y);
+    sub_lazy(c_fq, t, x, y);
 #pragma unroll
     for (int i = 0; i < NL; ++i) r[i] = t[i];
 }
 // lazy values live in [0, 2p): zero is 0 or p
 __device__ __forceinline__ bool fq_is_zero(const uint32_t *a) {
     bool all0 = true, allp = true;
-    for (int i = 0; i < NL; ++i) { all0 = all0 && a[i] == 0; allp = allp && a[i] == c_fp.p[i]; }
+    for (int i = 0; i < NL; ++i) { all0 = all0 && a[i] == 0; allp = allp && a[i] == c_fq.p[i]; }
     return all0 || allp;
 }
 __device__ __forceinline__ void fq_copy(uint32_t *r, const uint32_t *a) {
     for (int i = 0; i < NL; ++i) r[i] = a[i];
 }
 __device__ __forceinline__ void g1_set_identity(G1 &r) {
-    for (int i = 0; i < NL; ++i) { r.x[i] = 0; r.y[i] = c_fp.r1[i]; r.z[i] = 0; }
+    for (int i = 0; i < NL; ++i) { r.x[i] = 0; r.y[i] = c_fq.r1[i]; r.z[i] = 0; }
 }
 __device__ __forceinline__ void g1_copy(G1 &r, const G1 &a) { fq_copy(r.x, a.x); fq_copy(r.y, a.y); fq_copy(r.z, a.z); }
 
@@ -175,9 +181,9 @@ __global__ void __launch_bounds__(THREADS) g1_reduce_kernel(uint32_t *out, const
     }
     if (threadIdx.x == 0) {
         for (int i = 0; i < NL; ++i) { acc.x[i] = mine[i]; acc.y[i] = mine[NL + i]; acc.z[i] = mine[2 * NL + i]; }
-        canonicalize(acc.x);
-        canonicalize(acc.y);
-        canonicalize(acc.z);
+        canonicalize(c_fq, acc.x);
+        canonicalize(c_fq, acc.y);
+        canonicalize(c_fq, acc.z);
         g1_store(out, acc);
     }
 }

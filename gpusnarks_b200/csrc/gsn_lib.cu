@@ -16,6 +16,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_set>
 #include <vector>
 
@@ -70,8 +71,15 @@ struct Plan768 {
     std::vector<uint32_t> digits; // l_1..l_P
     uint32_t lmax = 0;
     DevBuf wloc;                  // w_T^k, k < T/2, T = 2^lmax
-    std::vector<std::unique_ptr<DevBuf>> pre;  // pre[q]: table read by pass q (nullptr if none)
+    // pre-twiddles of pass q (boundary q-1 | q): flat table (192 B per element index of the boundary's sub-problem)
+    // or, when that table would exceed the context's flat-table limit, the two-level tables below (two products)
+    std::vector<std::unique_ptr<DevBuf>> pre;  // pre[q]: flat table read by pass q (nullptr if none / two-level)
     std::vector<uint64_t> pre_mask;
+    std::vector<uint8_t> pre_two_level;        // pass q multiplies by t_lo[e & lomask] * t_hi[e >> lo_bits]
+    DevBuf t_lo, t_lo_scaled, t_hi;            // fixed-operand format; t_lo_scaled = n^-1 * t_lo (boundary 1 of a scaled plan)
+    uint32_t lo_bits = 0;
+    size_t table_bytes = 0;
+    uint64_t last_use = 0;
 };
 
 struct Plan32 {
@@ -103,58 +111,93 @@ std::vector<uint32_t> plan_digits(uint32_t logn, uint32_t max_log) {
 bool is_pow2(size_t n) { return n && !(n & (n - 1)); }
 uint32_t ilog2(size_t n) { uint32_t l = 0; while (((size_t)1 << l) < n) ++l; return l; }
 
+struct StreamWork {   // scratch buffer of the multi-pass transforms, one per stream that has used the context
+    cudaStream_t stream = nullptr;
+    DevBuf buf;
+    uint64_t last_use = 0;
+};
+
 }  // namespace
+
+struct gsn_coset_entry;
 
 struct gsn_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::mutex mu;
     int field = GSN_FIELD_MNT4753_FR;
-    gsn::FieldConstants768 fc;
+    gsn::FieldConstants768 fc;     // travels with every launch as a kernel parameter: per context, never uploaded
     gsn::host::Field768 hf;
     int two_adicity = 30;
-    DevBuf work;
+    std::vector<std::unique_ptr<StreamWork>> works;  // keyed by stream: concurrent streams never share scratch
     DevBuf io;   // device staging buffer of the host-pointer entry points (grown on demand, reused)
     DevBuf io2;  // second staging buffer: the batch entry point alternates between the two
     cudaEvent_t ev_io_free[2] = {nullptr, nullptr};  // D2H of the transform that last used io / io2 has finished
     std::vector<std::unique_ptr<Plan768>> plans768;
     std::vector<std::unique_ptr<Plan32>> plans32;
+    std::vector<std::unique_ptr<gsn_coset_entry>> cosets;   // cached coset shift tables (fourstep_host.inl)
+    size_t flat_table_limit = (size_t)4 << 30;   // a pre-twiddle table larger than this becomes two-level
+    size_t plan_cache_bytes = (size_t)16 << 30;  // least-recently-used 768-bit plans are dropped beyond this (and beyond 16 plans)
+    uint64_t use_clock = 0;
+    int v2_flags = gsn::V2_LAZY | gsn::V2_PREFETCH;  // large-tile kernel variant; -1 = always the small-tile kernel
     uint64_t launches = 0;
     int sm_count = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the pipelined host-pointer path
     cudaEvent_t ev_chunk[2][16] = {{nullptr}};
-    bool attr768_set = false, attr32_set = false;
     std::unordered_set<const void *> smem_configured;  // kernels whose dynamic shared-memory limit was raised on this device
+    // pinned bounce buffers of the pageable host path
+    void *bounce[2] = {nullptr, nullptr};
+    size_t bounce_bytes = 0;
+    gsn_ctx();
+    ~gsn_ctx();
 };
 
 namespace {
 
-int upload_field(gsn_ctx *ctx, int field) {
-    static const uint32_t fr_p[24] = GSN_FR_MOD, fr_p2[24] = GSN_FR_MOD2, fr_r1[24] = GSN_FR_R1, fr_r2[24] = GSN_FR_R2;
-    static const uint32_t fq_p[24] = GSN_FQ_MOD, fq_p2[24] = GSN_FQ_MOD2, fq_r1[24] = GSN_FQ_R1, fq_r2[24] = GSN_FQ_R2;
+int set_field(gsn_ctx *ctx, int field) {
+    static const uint32_t fr_p[24] = GSN_FR_MOD, fr_p2[24] = GSN_FR_MOD2, fr_p3[24] = GSN_FR_MOD3, fr_p6[24] = GSN_FR_MOD6, fr_r1[24] = GSN_FR_R1, fr_r2[24] = GSN_FR_R2;
+    static const uint32_t fq_p[24] = GSN_FQ_MOD, fq_p2[24] = GSN_FQ_MOD2, fq_p3[24] = GSN_FQ_MOD3, fq_p6[24] = GSN_FQ_MOD6, fq_r1[24] = GSN_FQ_R1, fq_r2[24] = GSN_FQ_R2;
     static const uint32_t fr_np[24] = GSN_FR_NPRIME768, fq_np[24] = GSN_FQ_NPRIME768;
     const bool fr = field == GSN_FIELD_MNT4753_FR;
+    memset(&ctx->fc, 0, sizeof(ctx->fc));
     memcpy(ctx->fc.p, fr ? fr_p : fq_p, 96);
     memcpy(ctx->fc.p2, fr ? fr_p2 : fq_p2, 96);
+    memcpy(ctx->fc.p3, fr ? fr_p3 : fq_p3, 96);
+    memcpy(ctx->fc.p6, fr ? fr_p6 : fq_p6, 96);
     memcpy(ctx->fc.r1, fr ? fr_r1 : fq_r1, 96);
     memcpy(ctx->fc.r2, fr ? fr_r2 : fq_r2, 96);
     ctx->fc.np0 = fr ? GSN_FR_NP0 : GSN_FQ_NP0;
+    ctx->fc.qmagic = fr ? GSN_FR_QMAGIC : GSN_FQ_QMAGIC;
     memcpy(ctx->fc.nprime, fr ? fr_np : fq_np, 96);
     ctx->two_adicity = fr ? GSN_FR_TWO_ADICITY : GSN_FQ_TWO_ADICITY;
     ctx->hf.init(ctx->fc.p, ctx->fc.r1);
     ctx->field = field;
-    CU(cudaMemcpyToSymbolAsync(gsn::c_fp, &ctx->fc, sizeof(ctx->fc), 0, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
     return GSN_OK;
 }
 
-int ensure_work(gsn_ctx *ctx, size_t bytes) {
-    if (ctx->work.bytes >= bytes) return GSN_OK;
-    if (ctx->work.p) { cudaFree(ctx->work.p); ctx->work.p = nullptr; ctx->work.bytes = 0; }
-    cudaError_t e = cudaMalloc(&ctx->work.p, bytes);
-    if (e != cudaSuccess) { cudaGetLastError(); return fail(GSN_ERR_TOO_LARGE, "workspace of %zu bytes: %s", bytes, cudaGetErrorString(e)); }
-    ctx->work.bytes = bytes;
+// scratch of `bytes` for work enqueued on stream st (kernels of different streams may run concurrently)
+int ensure_work(gsn_ctx *ctx, cudaStream_t st, size_t bytes, uint32_t **out) {
+    StreamWork *w = nullptr;
+    for (auto &sw : ctx->works) if (sw->stream == st) w = sw.get();
+    if (!w) {
+        if (ctx->works.size() >= 8) {  // drop the least recently used stream's scratch (cudaFree waits for its kernels)
+            size_t lru = 0;
+            for (size_t i = 1; i < ctx->works.size(); ++i) if (ctx->works[i]->last_use < ctx->works[lru]->last_use) lru = i;
+            ctx->works.erase(ctx->works.begin() + lru);
+        }
+        ctx->works.push_back(std::make_unique<StreamWork>());
+        w = ctx->works.back().get();
+        w->stream = st;
+    }
+    w->last_use = ++ctx->use_clock;
+    if (w->buf.bytes < bytes) {
+        if (w->buf.p) { cudaFree(w->buf.p); w->buf.p = nullptr; w->buf.bytes = 0; }
+        cudaError_t e = cudaMalloc(&w->buf.p, bytes);
+        if (e != cudaSuccess) { cudaGetLastError(); w->buf.p = nullptr; return fail(GSN_ERR_TOO_LARGE, "workspace of %zu bytes: %s", bytes, cudaGetErrorString(e)); }
+        w->buf.bytes = bytes;
+    }
+    *out = (uint32_t *)w->buf.p;
     return GSN_OK;
 }
 
@@ -176,9 +219,37 @@ int dev_alloc(DevBuf &b, size_t bytes) {
 
 // Montgomery-form table (count x 96 B) -> fixed-operand format (count x 192 B) used by the transform kernels
 int convert_to_shoup(gsn_ctx *ctx, uint32_t *d_out, const uint32_t *d_in, uint64_t count, cudaStream_t st) {
-    gsn::to_shoup_table768<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(d_out, d_in, count);
+    gsn::to_shoup_table768<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(ctx->fc, d_out, d_in, count);
     ctx->launches++;
     CU(cudaGetLastError());
+    return GSN_OK;
+}
+
+// Two-level power tables of `base` (Montgomery form, on the host) in fixed-operand format:
+//   t_lo[e] = scale * base^e, e < 2^lo_bits;   t_hi[e] = base^(e << lo_bits), e < 2^hi_bits     (scale may be null)
+// built on the device: per-thread square-and-multiply for the 2^lo_bits + 2^hi_bits entries.
+int build_two_level(gsn_ctx *ctx, const uint64_t *base_h, const uint64_t *scale_h, uint32_t lo_bits, uint32_t hi_bits, DevBuf &t_lo, DevBuf *t_lo_scaled,
+                    DevBuf &t_hi, cudaStream_t st) {
+    int rc;
+    DevBuf d_w, d_sc, lo_m, hi_m, lo_s;
+    const uint64_t nlo = 1ull << lo_bits, nhi = 1ull << hi_bits;
+    if ((rc = dev_alloc(d_w, 96)) || (rc = dev_alloc(lo_m, nlo * 96)) || (rc = dev_alloc(hi_m, nhi * 96))) return rc;
+    if ((rc = dev_alloc(t_lo, nlo * 192)) || (rc = dev_alloc(t_hi, nhi * 192))) return rc;
+    CU(cudaMemcpyAsync(d_w.p, base_h, 96, cudaMemcpyHostToDevice, st));
+    gsn::pow_table768<<<(unsigned)((nlo + 127) / 128), 128, 0, st>>>(ctx->fc, (uint32_t *)lo_m.p, (const uint32_t *)d_w.p, nlo, 1);
+    gsn::pow_table768<<<(unsigned)((nhi + 127) / 128), 128, 0, st>>>(ctx->fc, (uint32_t *)hi_m.p, (const uint32_t *)d_w.p, nhi, nlo);
+    ctx->launches += 2;
+    if ((rc = convert_to_shoup(ctx, (uint32_t *)t_lo.p, (const uint32_t *)lo_m.p, nlo, st))) return rc;
+    if ((rc = convert_to_shoup(ctx, (uint32_t *)t_hi.p, (const uint32_t *)hi_m.p, nhi, st))) return rc;
+    if (scale_h && t_lo_scaled) {
+        if ((rc = dev_alloc(d_sc, 96)) || (rc = dev_alloc(lo_s, nlo * 96)) || (rc = dev_alloc(*t_lo_scaled, nlo * 192))) return rc;
+        CU(cudaMemcpyAsync(d_sc.p, scale_h, 96, cudaMemcpyHostToDevice, st));
+        gsn::scale_table768<<<(unsigned)((nlo + 127) / 128), 128, 0, st>>>(ctx->fc, (uint32_t *)lo_s.p, (const uint32_t *)lo_m.p, (const uint32_t *)d_sc.p, nlo);
+        ctx->launches++;
+        if ((rc = convert_to_shoup(ctx, (uint32_t *)t_lo_scaled->p, (const uint32_t *)lo_s.p, nlo, st))) return rc;
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));  // the Montgomery-form temporaries are freed on return
     return GSN_OK;
 }
 
@@ -194,9 +265,24 @@ int validate_omega768(gsn_ctx *ctx, const uint32_t *omega, uint32_t logn) {
     return GSN_OK;
 }
 
+void evict_plans768(gsn_ctx *ctx, const Plan768 *keep) {
+    for (;;) {
+        size_t total = 0;
+        for (auto &pl : ctx->plans768) total += pl->table_bytes;
+        if (ctx->plans768.size() <= 16 && total <= ctx->plan_cache_bytes) return;
+        size_t lru = ctx->plans768.size();
+        for (size_t i = 0; i < ctx->plans768.size(); ++i)
+            if (ctx->plans768[i].get() != keep && (lru == ctx->plans768.size() || ctx->plans768[i]->last_use < ctx->plans768[lru]->last_use)) lru = i;
+        if (lru == ctx->plans768.size()) return;
+        cudaDeviceSynchronize();  // kernels in flight may still read the tables
+        ctx->plans768.erase(ctx->plans768.begin() + lru);
+    }
+}
+
 int get_plan768(gsn_ctx *ctx, uint32_t logn, const uint32_t *omega, int inverse, int scale, Plan768 **out) {
     for (auto &pl : ctx->plans768)
         if (pl->field == ctx->field && pl->logn == logn && pl->inverse == (inverse != 0) && pl->scale == (scale != 0) && memcmp(pl->omega, omega, 96) == 0) {
+            pl->last_use = ++ctx->use_clock;
             *out = pl.get();
             return GSN_OK;
         }
@@ -215,6 +301,7 @@ int get_plan768(gsn_ctx *ctx, uint32_t logn, const uint32_t *omega, int inverse,
     const size_t P = pl->digits.size();
     pl->pre.resize(P);
     pl->pre_mask.assign(P, 0);
+    pl->pre_two_level.assign(P, 0);
 
     const uint64_t n = 1ull << logn;
     // effective root (omega or omega^-1 = omega^(n-1)) and n^-1, Montgomery form, on the host
@@ -237,49 +324,70 @@ int get_plan768(gsn_ctx *ctx, uint32_t logn, const uint32_t *omega, int inverse,
     const uint64_t half = pl->lmax ? (1ull << (pl->lmax - 1)) : 1;
     DevBuf wloc_m;  // Montgomery form, converted below
     if ((rc = dev_alloc(wloc_m, half * 96)) || (rc = dev_alloc(pl->wloc, half * 192))) return rc;
-    gsn::pow_table768<<<(unsigned)((half + 127) / 128), 128, 0, st>>>((uint32_t *)wloc_m.p, (const uint32_t *)d_w.p, half,
+    pl->table_bytes += half * 192;
+    gsn::pow_table768<<<(unsigned)((half + 127) / 128), 128, 0, st>>>(ctx->fc, (uint32_t *)wloc_m.p, (const uint32_t *)d_w.p, half,
                                                                         pl->lmax ? (n >> pl->lmax) : 0);
     ctx->launches++;
     if ((rc = convert_to_shoup(ctx, (uint32_t *)pl->wloc.p, (const uint32_t *)wloc_m.p, half, st))) return rc;
     if (P > 1) {
-        const uint32_t lo_bits = std::min<uint32_t>(10, logn);
-        if ((rc = dev_alloc(t_lo, (1ull << lo_bits) * 96))) return rc;
-        if ((rc = dev_alloc(t_hi, (n >> lo_bits) * 96))) return rc;
-        gsn::pow_table768<<<(unsigned)(((1ull << lo_bits) + 127) / 128), 128, 0, st>>>((uint32_t *)t_lo.p, (const uint32_t *)d_w.p, 1ull << lo_bits, 1);
-        gsn::pow_table768<<<(unsigned)(((n >> lo_bits) + 127) / 128), 128, 0, st>>>((uint32_t *)t_hi.p, (const uint32_t *)d_w.p, n >> lo_bits, 1ull << lo_bits);
-        ctx->launches += 2;
-        // boundaries are built last-to-first so that, for an inverse plan, the low table can be
-        // scaled by n^-1 in place just before boundary 1 (which thereby carries the scaling)
-        for (size_t q = P - 1; q >= 1; --q) {
+        // which boundaries get a flat table (one product per element) and which the two-level tables (two products)
+        bool any_two_level = false, any_flat = false;
+        for (size_t q = 1; q < P; ++q) {
             uint32_t logN = 0;
             for (size_t i = q - 1; i < P; ++i) logN += pl->digits[i];
-            const uint32_t rest_bits = logN - pl->digits[q - 1];
-            if (q == 1 && scale) {
-                const uint64_t cnt = 1ull << lo_bits;
-                gsn::scale_table768<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>((uint32_t *)t_lo.p, (const uint32_t *)t_lo.p, (const uint32_t *)d_ninv.p, cnt);
+            pl->pre_two_level[q] = ((size_t)192 << logN) > ctx->flat_table_limit;
+            (pl->pre_two_level[q] ? any_two_level : any_flat) = true;
+        }
+        if (any_two_level) {
+            pl->lo_bits = (logn + 1) / 2;
+            if ((rc = build_two_level(ctx, w_eff, scale ? n_inv : nullptr, pl->lo_bits, logn - pl->lo_bits, pl->t_lo, &pl->t_lo_scaled, pl->t_hi, st))) return rc;
+            pl->table_bytes += pl->t_lo.bytes + pl->t_lo_scaled.bytes + pl->t_hi.bytes;
+        }
+        if (any_flat) {
+            const uint32_t lo_bits = std::min<uint32_t>(10, logn);
+            if ((rc = dev_alloc(t_lo, (1ull << lo_bits) * 96))) return rc;
+            if ((rc = dev_alloc(t_hi, (n >> lo_bits) * 96))) return rc;
+            gsn::pow_table768<<<(unsigned)(((1ull << lo_bits) + 127) / 128), 128, 0, st>>>(ctx->fc, (uint32_t *)t_lo.p, (const uint32_t *)d_w.p, 1ull << lo_bits, 1);
+            gsn::pow_table768<<<(unsigned)(((n >> lo_bits) + 127) / 128), 128, 0, st>>>(ctx->fc, (uint32_t *)t_hi.p, (const uint32_t *)d_w.p, n >> lo_bits, 1ull << lo_bits);
+            ctx->launches += 2;
+            // boundaries are built last-to-first so that, for an inverse plan, the low table can be
+            // scaled by n^-1 in place just before boundary 1 (which thereby carries the scaling)
+            for (size_t q = P - 1; q >= 1; --q) {
+                if (pl->pre_two_level[q]) continue;
+                uint32_t logN = 0;
+                for (size_t i = q - 1; i < P; ++i) logN += pl->digits[i];
+                const uint32_t rest_bits = logN - pl->digits[q - 1];
+                if (q == 1 && scale) {
+                    const uint64_t cnt = 1ull << lo_bits;
+                    gsn::scale_table768<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>(ctx->fc, (uint32_t *)t_lo.p, (const uint32_t *)t_lo.p, (const uint32_t *)d_ninv.p, cnt);
+                    ctx->launches++;
+                }
+                pl->pre[q] = std::make_unique<DevBuf>();
+                DevBuf pre_m;  // Montgomery form (transient), converted into the plan's table
+                if ((rc = dev_alloc(pre_m, (1ull << logN) * 96)) || (rc = dev_alloc(*pl->pre[q], (1ull << logN) * 192))) return rc;
+                pl->table_bytes += pl->pre[q]->bytes;
+                pl->pre_mask[q] = (1ull << logN) - 1;
+                const uint64_t cnt = 1ull << logN;
+                gsn::build_pretw768<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>(ctx->fc, (uint32_t *)pre_m.p, (const uint32_t *)t_lo.p, (const uint32_t *)t_hi.p,
+                                                                                    logN, rest_bits, logn - logN, lo_bits);
                 ctx->launches++;
+                if ((rc = convert_to_shoup(ctx, (uint32_t *)pl->pre[q]->p, (const uint32_t *)pre_m.p, cnt, st))) return rc;
+                CU(cudaStreamSynchronize(st));  // pre_m is freed at the end of this iteration
             }
-            pl->pre[q] = std::make_unique<DevBuf>();
-            DevBuf pre_m;  // Montgomery form (transient), converted into the plan's table
-            if ((rc = dev_alloc(pre_m, (1ull << logN) * 96)) || (rc = dev_alloc(*pl->pre[q], (1ull << logN) * 192))) return rc;
-            pl->pre_mask[q] = (1ull << logN) - 1;
-            const uint64_t cnt = 1ull << logN;
-            gsn::build_pretw768<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>((uint32_t *)pre_m.p, (const uint32_t *)t_lo.p, (const uint32_t *)t_hi.p,
-                                                                                logN, rest_bits, logn - logN, lo_bits);
-            ctx->launches++;
-            if ((rc = convert_to_shoup(ctx, (uint32_t *)pl->pre[q]->p, (const uint32_t *)pre_m.p, cnt, st))) return rc;
-            CU(cudaStreamSynchronize(st));  // pre_m is freed at the end of this iteration
         }
     } else if (scale) {
         pl->pre[0] = std::make_unique<DevBuf>();
         if ((rc = dev_alloc(*pl->pre[0], 192))) return rc;
+        pl->table_bytes += 192;
         if ((rc = convert_to_shoup(ctx, (uint32_t *)pl->pre[0]->p, (const uint32_t *)d_ninv.p, 1, st))) return rc;
         pl->pre_mask[0] = 0;
     }
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(st));
+    pl->last_use = ++ctx->use_clock;
     *out = pl.get();
     ctx->plans768.push_back(std::move(pl));
+    evict_plans768(ctx, *out);
     return GSN_OK;
 }
 
@@ -293,23 +401,65 @@ uint32_t choose_log_tile768(const gsn_ctx *ctx, const Plan768 *pl, uint64_t tota
     return log_tile;
 }
 
+// Pre-twiddle supplied by the caller of a transform (first pass): a flat table indexed by the element index, or
+// two-level tables of w^(k * r) with (k, r) cut out of the element index (four-step twiddles, coset shifts).
+struct ExtPre {
+    gsn::PreDesc pd;
+    bool present = false;
+};
+
+ExtPre ext_flat(const uint32_t *table) {
+    ExtPre e;
+    memset(&e.pd, 0, sizeof(e.pd));
+    if (table) {
+        e.present = true;
+        e.pd.mode = 1;
+        e.pd.tab = table;
+        e.pd.flat_mask = ~0ull;
+    }
+    return e;
+}
+
+struct WaitDesc {  // arrival flags of the fused four-step (see PassGeom::wait_flags)
+    const uint32_t *flags = nullptr;
+    uint32_t epoch = 0, shift = 0, mask = 0, first = 0;
+};
+
+template <int FLAGS>
+int launch_pass2(gsn_ctx *ctx, unsigned grid, size_t smem, cudaStream_t st, const uint32_t *src, uint32_t *dst, const uint32_t *wloc, const gsn::PassGeom &g,
+                 const gsn::PreDesc &pd, const gsn::PreDesc &post, const gsn::ScatterDesc &sc) {
+    auto kern = gsn::ntt768_pass2<FLAGS>;
+    if (!ctx->smem_configured.count((const void *)kern)) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << MAX_PASS_LOG) * gsn::SMEM_PITCH4 * 16));
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        ctx->smem_configured.insert((const void *)kern);
+    }
+    kern<<<grid, 256, smem, st>>>(src, dst, wloc, g, pd, post, sc, ctx->fc);
+    return GSN_OK;
+}
+
 // Launches passes [q_begin, q_end) of the plan; tile range [tile0, tile0 + ntiles) of each (ntiles == 0: all).
-int launch_ntt768_range(gsn_ctx *ctx, Plan768 *pl, uint32_t *d_data, size_t batch, uint32_t log_r, const uint32_t *ext_pre, cudaStream_t st,
-                        size_t q_begin, size_t q_end, uint64_t tile0, uint64_t ntiles, const gsn::ScatterDesc *scatter = nullptr) {
+int launch_ntt768_range(gsn_ctx *ctx, Plan768 *pl, uint32_t *d_data, size_t batch, uint32_t log_r, const ExtPre &ext, cudaStream_t st,
+                        size_t q_begin, size_t q_end, uint64_t tile0, uint64_t ntiles, const gsn::ScatterDesc *scatter = nullptr,
+                        const WaitDesc *wait = nullptr, const ExtPre *ext_post = nullptr) {
     const size_t P = pl->digits.size();
     const uint64_t total = (uint64_t)batch << (pl->logn + log_r);
     const uint32_t log_tile = choose_log_tile768(ctx, pl, total);
     int rc;
-    if (P > 1 && (rc = ensure_work(ctx, total * 96))) return rc;
-    uint32_t *work = (uint32_t *)ctx->work.p;
+    uint32_t *work = nullptr;
+    if (P > 1 && (rc = ensure_work(ctx, st, total * 96, &work))) return rc;
     gsn::ScatterDesc no_scatter;
     memset(&no_scatter, 0, sizeof(no_scatter));
 
-    auto kern = gsn::ntt768_pass<NTT768_THREADS, 2>;
-    if (!ctx->attr768_set) {
+    // kernel variant: 0..3 = warp-owned large-tile kernel (flag bits: 1 lazy ranges, 2 prefetch) for 1024-element tiles;
+    // 4 (or -1) = CTA-wide kernel, strict ranges; 5 = CTA-wide kernel, wide lazy ranges.  Smaller tiles always CTA-wide.
+    const int variant = ctx->v2_flags < 0 ? 4 : ctx->v2_flags;
+    const bool cta_lazy = variant == 5;
+    auto kern = cta_lazy ? gsn::ntt768_pass<NTT768_THREADS, 2, true> : gsn::ntt768_pass<NTT768_THREADS, 2, false>;
+    if (!ctx->smem_configured.count((const void *)kern)) {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << MAX_PASS_LOG) * gsn::SMEM_PITCH4 * 16));
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        ctx->attr768_set = true;
+        ctx->smem_configured.insert((const void *)kern);
     }
     uint32_t below = log_r;
     for (size_t i = 0; i < P; ++i) below += pl->digits[i];
@@ -321,31 +471,78 @@ int launch_ntt768_range(gsn_ctx *ctx, Plan768 *pl, uint32_t *d_data, size_t batc
         g.log_l = pl->digits[q];
         g.log_s = below;
         g.log_r = log_r;
-        g.pre_shift = log_r;
         g.tile0 = (uint32_t)tile0;
         g.log_tile = log_tile;
         g.wloc_shift = pl->lmax - pl->digits[q];
         g.final_natural = q + 1 == P;
         g.canonical = q + 1 == P;
-        g.ndig = (uint32_t)P;
-        for (size_t i = 0; i < P; ++i) g.dig[i] = pl->digits[i];
         g.logn = pl->logn;
-        g.has_pre = pl->pre[q] != nullptr;
-        g.pre_mask = pl->pre_mask[q];
-        const uint32_t *pre = g.has_pre ? (const uint32_t *)pl->pre[q]->p : nullptr;
-        if (q == 0 && ext_pre) {  // caller-supplied table indexed by the element index (four-step twiddles)
-            g.has_pre = 1;
-            g.pre_mask = ~0ull;
-            g.pre_shift = 0;
-            pre = ext_pre;
+        if (g.final_natural) {  // output digits in reversed significance: (k_P .. k_1)
+            uint32_t shift = 0, pos = pl->logn - pl->digits[P - 1];
+            for (size_t i = 0; i + 1 < P; ++i) {
+                pos -= pl->digits[i];
+                g.dpos[i] = pos;
+                g.dmask[i] = (1u << pl->digits[i]) - 1;
+                g.dshift[i] = shift;
+                shift += pl->digits[i];
+            }
+            g.kshift = shift;
         }
+        if (wait && q == 0 && wait->flags) {
+            g.wait_flags = wait->flags;
+            g.wait_epoch = wait->epoch;
+            g.wait_shift = wait->shift;
+            g.wait_mask = wait->mask;
+            g.wait_first = wait->first;
+        }
+        gsn::PreDesc pd;
+        memset(&pd, 0, sizeof(pd));
+        if (q == 0 && ext.present) {
+            pd = ext.pd;  // caller-supplied pre-twiddle (four-step twiddles, coset shifts)
+        } else if (pl->pre[q]) {
+            pd.mode = 1;
+            pd.tab = (const uint32_t *)pl->pre[q]->p;
+            pd.flat_shift = log_r;
+            pd.flat_mask = pl->pre_mask[q];
+        } else if (q > 0 && pl->pre_two_level[q]) {
+            // boundary q-1 | q of the sub-problem of size N = 2^(l_{q-1} + ... + l_P): w_N^(k * rest)
+            uint32_t logN = 0;
+            for (size_t i = q - 1; i < P; ++i) logN += pl->digits[i];
+            const uint32_t rest_bits = logN - pl->digits[q - 1];
+            pd.mode = 2;
+            pd.tab = (const uint32_t *)((q == 1 && pl->scale) ? pl->t_lo_scaled.p : pl->t_lo.p);
+            pd.tab_hi = (const uint32_t *)pl->t_hi.p;
+            pd.k_shift = log_r + rest_bits;
+            pd.k_mask = (1ull << pl->digits[q - 1]) - 1;
+            pd.r_shift = log_r;
+            pd.r_mask = (1ull << rest_bits) - 1;
+            pd.logN = logN;
+            pd.exp_shift = pl->logn - logN;
+            pd.lo_bits = pl->lo_bits;
+        }
+        gsn::PreDesc post;
+        memset(&post, 0, sizeof(post));
+        if (q + 1 == P && ext_post && ext_post->present) post = ext_post->pd;  // caller-supplied post-twiddle, indexed by the output index
         // pass 1 reads the caller's buffer, the last pass writes it; middle passes run in
         // place in the workspace (a tile reads and writes the same index set).
         const uint32_t *src = q == 0 ? d_data : work;
         uint32_t *dst = (q + 1 == P) ? d_data : work;
         const size_t smem = ((size_t)1 << log_tile) * gsn::SMEM_PITCH4 * 16;
-        kern<<<(unsigned)(ntiles ? ntiles : (total >> log_tile)), NTT768_THREADS, smem, st>>>(src, dst, (const uint32_t *)pl->wloc.p, pre, g,
-                                                                                                         (scatter && q + 1 == P) ? *scatter : no_scatter);
+        const unsigned grid = (unsigned)(ntiles ? ntiles : (total >> log_tile));
+        const gsn::ScatterDesc &sc = (scatter && q + 1 == P) ? *scatter : no_scatter;
+        const uint32_t *wloc = (const uint32_t *)pl->wloc.p;
+        if (log_tile == 10 && g.log_l >= 1 && variant < 4) {
+            switch (variant) {
+                case 0: rc = launch_pass2<0>(ctx, grid, smem, st, src, dst, wloc, g, pd, post, sc); break;
+                case 1: rc = launch_pass2<1>(ctx, grid, smem, st, src, dst, wloc, g, pd, post, sc); break;
+                case 2: rc = launch_pass2<2>(ctx, grid, smem, st, src, dst, wloc, g, pd, post, sc); break;
+                default: rc = launch_pass2<3>(ctx, grid, smem, st, src, dst, wloc, g, pd, post, sc); break;
+            }
+            if (rc) return rc;
+        } else {
+            if (g.wait_flags) return fail(GSN_ERR_INVALID_ARG, "arrival flags need the large-tile kernel");
+            kern<<<grid, NTT768_THREADS, smem, st>>>(src, dst, wloc, g, pd, post, sc, ctx->fc);
+        }
         ctx->launches++;
     }
     CU(cudaGetLastError());
@@ -353,7 +550,7 @@ int launch_ntt768_range(gsn_ctx *ctx, Plan768 *pl, uint32_t *d_data, size_t batc
 }
 
 int launch_ntt768(gsn_ctx *ctx, Plan768 *pl, uint32_t *d_data, size_t batch, uint32_t log_r, const uint32_t *ext_pre, cudaStream_t st) {
-    return launch_ntt768_range(ctx, pl, d_data, batch, log_r, ext_pre, st, 0, pl->digits.size(), 0, 0);
+    return launch_ntt768_range(ctx, pl, d_data, batch, log_r, ext_flat(ext_pre), st, 0, pl->digits.size(), 0, 0);
 }
 
 int check_n(size_t n, size_t batch) {
@@ -365,6 +562,10 @@ int check_n(size_t n, size_t batch) {
 }  // namespace
 
 #include "ntt32_host.inl"
+#include "fourstep_host.inl"
+
+gsn_ctx::gsn_ctx() = default;
+gsn_ctx::~gsn_ctx() = default;
 
 extern "C" {
 
@@ -402,8 +603,10 @@ int gsn_ctx_create(gsn_ctx **out, int device) {
     for (int d = 0; d < 2; ++d)
         for (int i = 0; i < 16; ++i) CU(cudaEventCreateWithFlags(&ctx->ev_chunk[d][i], cudaEventDisableTiming));
     for (int d = 0; d < 2; ++d) CU(cudaEventCreateWithFlags(&ctx->ev_io_free[d], cudaEventDisableTiming));
-    int rc = upload_field(ctx.get(), GSN_FIELD_MNT4753_FR);
+    int rc = set_field(ctx.get(), GSN_FIELD_MNT4753_FR);
     if (rc) return rc;
+    if (const char *v = getenv("GSN_NTT768_VARIANT")) ctx->v2_flags = atoi(v);           // -1 small-tile kernel only, 0..3 flags of ntt768_pass2
+    if (const char *v = getenv("GSN_FLAT_TABLE_LIMIT")) ctx->flat_table_limit = strtoull(v, nullptr, 10);
     *out = ctx.release();
     return GSN_OK;
 }
@@ -412,8 +615,12 @@ int gsn_ctx_destroy(gsn_ctx *ctx) {
     if (!ctx) return GSN_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    cudaDeviceSynchronize();
     ctx->plans768.clear();
     ctx->plans32.clear();
+    ctx->cosets.clear();
+    ctx->works.clear();
+    for (int b = 0; b < 2; ++b) if (ctx->bounce[b]) cudaFreeHost(ctx->bounce[b]);
     for (int d = 0; d < 2; ++d)
         for (int i = 0; i < 16; ++i) if (ctx->ev_chunk[d][i]) cudaEventDestroy(ctx->ev_chunk[d][i]);
     for (int d = 0; d < 2; ++d) if (ctx->ev_io_free[d]) cudaEventDestroy(ctx->ev_io_free[d]);
@@ -430,10 +637,11 @@ int gsn_ctx_trim(gsn_ctx *ctx) {
     if (!ctx) return fail(GSN_ERR_INVALID_ARG, "null ctx");
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->device));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaDeviceSynchronize());  // caller streams may still be running transforms that use the tables / scratch
     ctx->plans768.clear();
     ctx->plans32.clear();
-    if (ctx->work.p) { cudaFree(ctx->work.p); ctx->work.p = nullptr; ctx->work.bytes = 0; }
+    ctx->cosets.clear();
+    ctx->works.clear();
     if (ctx->io.p) { cudaFree(ctx->io.p); ctx->io.p = nullptr; ctx->io.bytes = 0; }
     if (ctx->io2.p) { cudaFree(ctx->io2.p); ctx->io2.p = nullptr; ctx->io2.bytes = 0; }
     return GSN_OK;
@@ -449,8 +657,43 @@ int gsn_set_field768(gsn_ctx *ctx, int field) {
     if (!ctx) return fail(GSN_ERR_INVALID_ARG, "null ctx");
     if (field != GSN_FIELD_MNT4753_FR && field != GSN_FIELD_MNT4753_FQ) return fail(GSN_ERR_INVALID_ARG, "unknown field %d", field);
     std::lock_guard<std::mutex> lk(ctx->mu);
+    return set_field(ctx, field);  // host-side only: the constants travel with each launch, other contexts are unaffected
+}
+
+int gsn_ctx_set_option(gsn_ctx *ctx, int option, uint64_t value) {
+    if (!ctx) return fail(GSN_ERR_INVALID_ARG, "null ctx");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    switch (option) {
+        case GSN_OPT_FLAT_TABLE_LIMIT: ctx->flat_table_limit = (size_t)value; break;
+        case GSN_OPT_PLAN_CACHE_BYTES:
+            ctx->plan_cache_bytes = (size_t)value;
+            CU(cudaSetDevice(ctx->device));
+            evict_plans768(ctx, nullptr);
+            break;
+        case GSN_OPT_KERNEL_VARIANT:
+            if ((int64_t)value < -1 || (int64_t)value > 5) return fail(GSN_ERR_INVALID_ARG, "kernel variant %lld", (long long)value);
+            ctx->v2_flags = (int)(int64_t)value;
+            break;
+        default: return fail(GSN_ERR_INVALID_ARG, "unknown option %d", option);
+    }
+    return GSN_OK;
+}
+
+int gsn_ntt768_plan_info(gsn_ctx *ctx, size_t n, const uint32_t *omega, int inverse, uint64_t *table_bytes, unsigned *passes,
+                         unsigned *two_level_boundaries, uint64_t *cached_plans, uint64_t *cached_bytes) {
+    if (!ctx || !omega) return fail(GSN_ERR_INVALID_ARG, "null argument");
+    int rc = check_n(n, 1);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->device));
-    return upload_field(ctx, field);
+    Plan768 *pl;
+    if ((rc = get_plan768(ctx, ilog2(n), omega, inverse, inverse, &pl))) return rc;
+    if (table_bytes) *table_bytes = pl->table_bytes;
+    if (passes) *passes = (unsigned)pl->digits.size();
+    if (two_level_boundaries) { *two_level_boundaries = 0; for (auto f : pl->pre_two_level) *two_level_boundaries += f; }
+    if (cached_plans) *cached_plans = ctx->plans768.size();
+    if (cached_bytes) { *cached_bytes = 0; for (auto &q : ctx->plans768) *cached_bytes += q->table_bytes; }
+    return GSN_OK;
 }
 
 int gsn_ntt768_prepare(gsn_ctx *ctx, size_t n, size_t batch, const uint32_t *omega, int inverse) {
@@ -461,7 +704,8 @@ int gsn_ntt768_prepare(gsn_ctx *ctx, size_t n, size_t batch, const uint32_t *ome
     CU(cudaSetDevice(ctx->device));
     Plan768 *pl;
     if ((rc = get_plan768(ctx, ilog2(n), omega, inverse, inverse, &pl))) return rc;
-    if (pl->digits.size() > 1) return ensure_work(ctx, (size_t)batch * n * 96);
+    uint32_t *work;
+    if (pl->digits.size() > 1) return ensure_work(ctx, ctx->stream, (size_t)batch * n * 96, &work);
     return GSN_OK;
 }
 
@@ -522,7 +766,8 @@ static int enqueue_ntt768_host(gsn_ctx *ctx, Plan768 *pl, uint32_t *limbs, size_
     int chunks = 8;
     while (chunks > 1 && (cols_in % chunks || cols_out % chunks || tiles % chunks || (cols_in / chunks) * rows_in < 1024 ||
                           (cols_out / chunks) * (1ull << lP) < 1024)) chunks >>= 1;
-    if ((rc = ensure_work(ctx, n * 96))) return rc;
+    uint32_t *work_unused;
+    if ((rc = ensure_work(ctx, st, n * 96, &work_unused))) return rc;
     if (first) {  // order the copy-in stream after earlier (asynchronous, device-pointer) work on the context; later
                   // transforms of a batch must NOT wait for the compute stream, or their H2D could not overlap it
         CU(cudaEventRecord(ctx->ev0, st));
@@ -534,13 +779,13 @@ static int enqueue_ntt768_host(gsn_ctx *ctx, Plan768 *pl, uint32_t *limbs, size_
         CU(cudaEventRecord(ctx->ev_chunk[0][c], ctx->s_in));
         CU(cudaStreamWaitEvent(st, ctx->ev_chunk[0][c], 0));
         // pass 1 tiles of this column block: tile t covers sub-transforms (= columns) [t * 2^(log_tile-l1), ...)
-        if ((rc = launch_ntt768_range(ctx, pl, io, 1, 0, nullptr, st, 0, 1, c * tiles_per_chunk, tiles_per_chunk))) return rc;
+        if ((rc = launch_ntt768_range(ctx, pl, io, 1, 0, ext_flat(nullptr), st, 0, 1, c * tiles_per_chunk, tiles_per_chunk))) return rc;
     }
-    if (P > 2 && (rc = launch_ntt768_range(ctx, pl, io, 1, 0, nullptr, st, 1, P - 1, 0, 0))) return rc;
+    if (P > 2 && (rc = launch_ntt768_range(ctx, pl, io, 1, 0, ext_flat(nullptr), st, 1, P - 1, 0, 0))) return rc;
     for (int c = 0; c < chunks; ++c) {
         // last pass: sub-transform index t = (k_1, k_2, ...) with k_1 most significant, so a contiguous tile
         // range is a k_1 range = a column block of the output view
-        if ((rc = launch_ntt768_range(ctx, pl, io, 1, 0, nullptr, st, P - 1, P, c * tiles_per_chunk, tiles_per_chunk))) return rc;
+        if ((rc = launch_ntt768_range(ctx, pl, io, 1, 0, ext_flat(nullptr), st, P - 1, P, c * tiles_per_chunk, tiles_per_chunk))) return rc;
         CU(cudaEventRecord(ctx->ev_chunk[1][c], st));
         CU(cudaStreamWaitEvent(ctx->s_out, ctx->ev_chunk[1][c], 0));
         CU(cudaMemcpy2DAsync(limbs + c * cw_out * 24, cols_out * 96, io + c * cw_out * 24, cols_out * 96, cw_out * 96, rows_out, cudaMemcpyDeviceToHost, ctx->s_out));
@@ -548,6 +793,71 @@ static int enqueue_ntt768_host(gsn_ctx *ctx, Plan768 *pl, uint32_t *limbs, size_
     if (ev_free) {
         CU(cudaEventRecord(ev_free, ctx->s_out));
     }
+    return GSN_OK;
+}
+
+// Pageable host memory (what a std::vector hands us): a DMA from it is staged by the driver through one small pinned
+// buffer, at a fraction of the PCIe rate.  Here the staging is ours: two pinned bounce buffers per direction, filled /
+// drained by a few host threads (memcpy at memory speed) while the DMA engine moves the other one.
+static bool is_pageable(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+static void parallel_memcpy(void *dst, const void *src, size_t bytes) {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t nt = std::max<size_t>(1, std::min<size_t>({(size_t)4, (size_t)hw, bytes >> 20}));
+    if (nt == 1) { memcpy(dst, src, bytes); return; }
+    const size_t per = ((bytes / nt) + 4095) & ~(size_t)4095;
+    std::vector<std::thread> ts;
+    for (size_t t = 1; t < nt; ++t) {
+        const size_t off = t * per, len = off >= bytes ? 0 : std::min(per, bytes - off);
+        if (len) ts.emplace_back([=] { memcpy((char *)dst + off, (const char *)src + off, len); });
+    }
+    memcpy(dst, src, std::min(per, bytes));
+    for (auto &t : ts) t.join();
+}
+
+static int ntt768_host_pageable(gsn_ctx *ctx, Plan768 *pl, uint32_t *limbs, size_t n) {
+    int rc;
+    const size_t bytes = n * 96, chunk = (size_t)16 << 20;
+    if ((rc = ensure_io(ctx, bytes))) return rc;
+    if (ctx->bounce_bytes < chunk) {
+        for (int b = 0; b < 2; ++b) {
+            if (ctx->bounce[b]) cudaFreeHost(ctx->bounce[b]);
+            CU(cudaHostAlloc(&ctx->bounce[b], chunk, cudaHostAllocDefault));
+        }
+        ctx->bounce_bytes = chunk;
+    }
+    char *dev = (char *)ctx->io.p, *host = (char *)limbs;
+    cudaStream_t st = ctx->stream;
+    size_t k = 0;
+    for (size_t off = 0; off < bytes; off += chunk, ++k) {
+        const size_t len = std::min(chunk, bytes - off);
+        const int b = (int)(k & 1);
+        if (k >= 2) CU(cudaEventSynchronize(ctx->ev_chunk[0][b]));   // the DMA that last read this bounce buffer is done
+        parallel_memcpy(ctx->bounce[b], host + off, len);
+        CU(cudaMemcpyAsync(dev + off, ctx->bounce[b], len, cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(ctx->ev_chunk[0][b], st));
+    }
+    if ((rc = launch_ntt768(ctx, pl, (uint32_t *)dev, 1, 0, nullptr, st))) return rc;
+    // copy out: DMA of chunk k+1 overlaps the host memcpy of chunk k
+    const size_t nchunks = (bytes + chunk - 1) / chunk;
+    for (size_t c = 0; c < std::min<size_t>(2, nchunks); ++c) {
+        CU(cudaMemcpyAsync(ctx->bounce[c & 1], dev + c * chunk, std::min(chunk, bytes - c * chunk), cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(ctx->ev_chunk[1][c & 1], st));
+    }
+    for (size_t c = 0; c < nchunks; ++c) {
+        const int b = (int)(c & 1);
+        CU(cudaEventSynchronize(ctx->ev_chunk[1][b]));
+        parallel_memcpy(host + c * chunk, ctx->bounce[b], std::min(chunk, bytes - c * chunk));
+        if (c + 2 < nchunks) {
+            CU(cudaMemcpyAsync(ctx->bounce[b], dev + (c + 2) * chunk, std::min(chunk, bytes - (c + 2) * chunk), cudaMemcpyDeviceToHost, st));
+            CU(cudaEventRecord(ctx->ev_chunk[1][b], st));
+        }
+    }
+    CU(cudaStreamSynchronize(st));
     return GSN_OK;
 }
 
@@ -562,6 +872,15 @@ int gsn_ntt768_host_batch(gsn_ctx *ctx, uint32_t *const *limbs, size_t count, si
     CU(cudaSetDevice(ctx->device));
     Plan768 *pl;
     if ((rc = get_plan768(ctx, ilog2(n), omega, inverse, inverse, &pl))) return rc;
+    if (n * 96 >= ((size_t)4 << 20)) {   // large pageable vectors go through our own pinned bounce buffers
+        bool pageable = false;
+        for (size_t i = 0; i < count; ++i) pageable = pageable || is_pageable(limbs[i]);
+        if (pageable) {
+            for (size_t i = 0; i < count; ++i)
+                if ((rc = ntt768_host_pageable(ctx, pl, limbs[i], n))) return rc;
+            return GSN_OK;
+        }
+    }
     if ((rc = ensure_io(ctx, n * 96))) return rc;
     if (count > 1) {
         if (ctx->io2.bytes < n * 96) {
@@ -612,7 +931,7 @@ int gsn_fp768_binop_device(gsn_ctx *ctx, int op, uint32_t *d_out, const uint32_t
     if (count == 0) return GSN_OK;
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->device));
-    gsn::binop768<<<(unsigned)((count + 127) / 128), 128, 0, stream ? (cudaStream_t)stream : ctx->stream>>>(d_out, d_a, d_b, count, op);
+    gsn::binop768<<<(unsigned)((count + 127) / 128), 128, 0, stream ? (cudaStream_t)stream : ctx->stream>>>(ctx->fc, d_out, d_a, d_b, count, op);
     ctx->launches++;
     CU(cudaGetLastError());
     return GSN_OK;
@@ -631,7 +950,7 @@ int gsn_fp768_powers_device(gsn_ctx *ctx, uint32_t *d_table, size_t count, const
     memcpy(h, base, 96);
     memcpy(h + 24, scale ? scale : ctx->fc.r1, 96);
     CU(cudaMemcpyAsync(d_bs.p, h, 192, cudaMemcpyHostToDevice, st));
-    gsn::powers768<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(d_table, (const uint32_t *)d_bs.p, (const uint32_t *)d_bs.p + 24, count);
+    gsn::powers768<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(ctx->fc, d_table, (const uint32_t *)d_bs.p, (const uint32_t *)d_bs.p + 24, count);
     ctx->launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(st));  // d_bs is freed on return
@@ -653,10 +972,11 @@ int gsn_fp768_inner_product_device(gsn_ctx *ctx, uint32_t *d_out, const uint32_t
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     const unsigned blocks = (unsigned)std::min<size_t>((count + 127) / 128, (size_t)ctx->sm_count * 8);
     int rc;
-    if ((rc = ensure_work(ctx, (size_t)std::max(1u, blocks) * 96))) return rc;
+    uint32_t *work;
+    if ((rc = ensure_work(ctx, st, (size_t)std::max(1u, blocks) * 96, &work))) return rc;
     if (count == 0) { CU(cudaMemsetAsync(d_out, 0, 96, st)); return GSN_OK; }
-    gsn::inner_product768<128><<<blocks, 128, 0, st>>>((uint32_t *)ctx->work.p, d_a, d_b, count);
-    gsn::inner_product768<128><<<1, 128, 0, st>>>(d_out, (const uint32_t *)ctx->work.p, nullptr, blocks);
+    gsn::inner_product768<128><<<blocks, 128, 0, st>>>(ctx->fc, work, d_a, d_b, count);
+    gsn::inner_product768<128><<<1, 128, 0, st>>>(ctx->fc, d_out, work, nullptr, blocks);
     ctx->launches += 2;
     CU(cudaGetLastError());
     return GSN_OK;
@@ -684,11 +1004,10 @@ int gsn_g1_multiexp_device(gsn_ctx *ctx, uint32_t *d_out, const uint32_t *d_poin
     if (!ctx || !d_out || !d_points || !d_scalars) return fail(GSN_ERR_INVALID_ARG, "null argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->device));
-    if (ctx->field != GSN_FIELD_MNT4753_FQ)
-        return fail(GSN_ERR_INVALID_ARG, "G1 arithmetic lives over MNT4-753 Fq: call gsn_set_field768(ctx, GSN_FIELD_MNT4753_FQ) first");
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     int rc;
-    if ((rc = ensure_work(ctx, std::max<size_t>(n, 1) * 288))) return rc;
+    uint32_t *work;
+    if ((rc = ensure_work(ctx, st, std::max<size_t>(n, 1) * 288, &work))) return rc;
     constexpr int RT = 128;
     auto red = gsn::g1_reduce_kernel<RT>;
     if (!ctx->smem_configured.count((const void *)red)) {
@@ -696,10 +1015,10 @@ int gsn_g1_multiexp_device(gsn_ctx *ctx, uint32_t *d_out, const uint32_t *d_poin
         ctx->smem_configured.insert((const void *)red);
     }
     if (n) {
-        gsn::g1_scalar_mul_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((uint32_t *)ctx->work.p, d_points, d_scalars, n);
+        gsn::g1_scalar_mul_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(work, d_points, d_scalars, n);
         ctx->launches++;
     }
-    red<<<1, RT, RT * 288, st>>>(d_out, (const uint32_t *)ctx->work.p, n);
+    red<<<1, RT, RT * 288, st>>>(d_out, work, n);
     ctx->launches++;
     CU(cudaGetLastError());
     return GSN_OK;
@@ -734,7 +1053,7 @@ int gsn_fp768_binop_host(gsn_ctx *ctx, int op, uint32_t *out, const uint32_t *a,
     if ((rc = dev_alloc(da, count * 96)) || (rc = dev_alloc(db, count * 96)) || (rc = dev_alloc(dc, count * 96))) return rc;
     CU(cudaMemcpyAsync(da.p, a, count * 96, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(db.p, b, count * 96, cudaMemcpyHostToDevice, ctx->stream));
-    gsn::binop768<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>((uint32_t *)dc.p, (const uint32_t *)da.p, (const uint32_t *)db.p, count, op);
+    gsn::binop768<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(ctx->fc, (uint32_t *)dc.p, (const uint32_t *)da.p, (const uint32_t *)db.p, count, op);
     ctx->launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, dc.p, count * 96, cudaMemcpyDeviceToHost, ctx->stream));
@@ -767,7 +1086,7 @@ int gsn_ntt768_device_scatter(gsn_ctx *ctx, const uint32_t *d_limbs, size_t n, s
     sc.ins_shift = ins_shift;
     sc.my_rank = my_rank;
     // the source is only read: pass 1 goes to the workspace (or, for a one-pass plan, straight to the peers)
-    return launch_ntt768_range(ctx, pl, const_cast<uint32_t *>(d_limbs), batch, log_r, d_pre_table, stream ? (cudaStream_t)stream : ctx->stream, 0,
+    return launch_ntt768_range(ctx, pl, const_cast<uint32_t *>(d_limbs), batch, log_r, ext_flat(d_pre_table), stream ? (cudaStream_t)stream : ctx->stream, 0,
                                pl->digits.size(), 0, 0, &sc);
 }
 
@@ -782,7 +1101,7 @@ int gsn_peer_barrier(gsn_ctx *ctx, uint32_t *const *peer_flags, unsigned n_peers
         if (!peer_flags[r]) return fail(GSN_ERR_INVALID_ARG, "peer_flags[%u] is null", r);
         pf.flags[r] = peer_flags[r];
     }
-    gsn::peer_barrier_kernel<<<1, 32, 0, stream ? (cudaStream_t)stream : ctx->stream>>>(pf, n_peers, my_rank, epoch);
+    gsn::peer_barrier_kernel<<<1, 32, 0, stream ? (cudaStream_t)stream : ctx->stream>>>(pf, n_peers, my_rank, epoch, 1u);
     ctx->launches++;
     CU(cudaGetLastError());
     return GSN_OK;
@@ -837,20 +1156,20 @@ int gsn_fourstep_table768(gsn_ctx *ctx, uint32_t *d_table, size_t rows, size_t c
     DevBuf d_w, d_sc, t_lo, t_hi;
     if ((rc = dev_alloc(d_w, 96)) || (rc = dev_alloc(t_lo, (1ull << lo_bits) * 96)) || (rc = dev_alloc(t_hi, (n_total >> lo_bits) * 96))) return rc;
     CU(cudaMemcpyAsync(d_w.p, w_eff, 96, cudaMemcpyHostToDevice, st));
-    gsn::pow_table768<<<(unsigned)(((1ull << lo_bits) + 127) / 128), 128, 0, st>>>((uint32_t *)t_lo.p, (const uint32_t *)d_w.p, 1ull << lo_bits, 1);
-    gsn::pow_table768<<<(unsigned)(((n_total >> lo_bits) + 127) / 128), 128, 0, st>>>((uint32_t *)t_hi.p, (const uint32_t *)d_w.p, n_total >> lo_bits, 1ull << lo_bits);
+    gsn::pow_table768<<<(unsigned)(((1ull << lo_bits) + 127) / 128), 128, 0, st>>>(ctx->fc, (uint32_t *)t_lo.p, (const uint32_t *)d_w.p, 1ull << lo_bits, 1);
+    gsn::pow_table768<<<(unsigned)(((n_total >> lo_bits) + 127) / 128), 128, 0, st>>>(ctx->fc, (uint32_t *)t_hi.p, (const uint32_t *)d_w.p, n_total >> lo_bits, 1ull << lo_bits);
     ctx->launches += 2;
     if (scale) {
         if ((rc = dev_alloc(d_sc, 96))) return rc;
         CU(cudaMemcpyAsync(d_sc.p, sc, 96, cudaMemcpyHostToDevice, st));
         const uint64_t cnt = 1ull << lo_bits;
-        gsn::scale_table768<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>((uint32_t *)t_lo.p, (const uint32_t *)t_lo.p, (const uint32_t *)d_sc.p, cnt);
+        gsn::scale_table768<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>(ctx->fc, (uint32_t *)t_lo.p, (const uint32_t *)t_lo.p, (const uint32_t *)d_sc.p, cnt);
         ctx->launches++;
     }
     const uint64_t cnt = (uint64_t)rows * cols;
     DevBuf tab_m;  // Montgomery form, converted into the caller's table (fixed-operand format, 192 B per entry)
     if ((rc = dev_alloc(tab_m, cnt * 96))) return rc;
-    gsn::build_fourstep768<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>((uint32_t *)tab_m.p, (const uint32_t *)t_lo.p, (const uint32_t *)t_hi.p, rows, cols,
+    gsn::build_fourstep768<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>(ctx->fc, (uint32_t *)tab_m.p, (const uint32_t *)t_lo.p, (const uint32_t *)t_hi.p, rows, cols,
                                                                            row0, col0, logn, lo_bits);
     ctx->launches++;
     if ((rc = convert_to_shoup(ctx, d_table, (const uint32_t *)tab_m.p, cnt, st))) return rc;

@@ -11,7 +11,47 @@
 // four-step pre-twiddle on load, digit-reversed store in the last pass.
 #pragma once
 #include <cstdint>
-#include "ntt768.cuh"  // PassGeom, elem_index, out_index
+#include "ntt768.cuh"
+
+namespace gsn {
+// geometry of one 32-bit pass (same index math as the 768-bit PassGeom, tools/model_passes.py)
+struct PassGeom32 {
+    uint32_t log_l;          // stages of this pass (digit width)
+    uint32_t log_s;          // log2 stride (elements) of this digit
+    uint32_t log_r;          // log2 inner stride
+    uint32_t pre_shift;      // pre-twiddle index = (element index >> pre_shift) & pre_mask
+    uint32_t log_tile;       // log2 elements per CTA tile (>= log_l)
+    uint32_t wloc_shift;     // local table index = (jj << (log_l - s)) << wloc_shift
+    uint32_t final_natural;  // last pass: write digits reversed
+    uint32_t canonical;
+    uint32_t ndig;           // number of digits of the whole transform
+    uint32_t dig[4];         // digit widths l_1..l_P
+    uint32_t logn;           // sum of digits
+    uint32_t has_pre;        // pre-twiddle table present
+    uint32_t tile0;
+    uint64_t pre_mask;       // 0 => scalar pre-multiply (pre_tw[0])
+};
+__device__ __forceinline__ uint64_t elem_index(const PassGeom32 &g, uint64_t t, uint32_t j) {
+    const uint64_t o = t >> g.log_s, rlow = t & ((1ull << g.log_s) - 1);
+    return (((o << g.log_l) | j) << g.log_s) | rlow;
+}
+__device__ __forceinline__ uint64_t out_index(const PassGeom32 &g, uint64_t t, uint32_t k) {
+    if (!g.final_natural) return elem_index(g, t, k);
+    const uint64_t o = t >> g.log_s, rlow = t & ((1ull << g.log_s) - 1);
+    const uint32_t inner_bits = g.logn - g.log_l;
+    const uint64_t batch = o >> inner_bits;
+    const uint64_t rest = o & ((1ull << inner_bits) - 1);
+    uint64_t out = 0;
+    uint32_t shift = 0, pos = inner_bits;
+    for (uint32_t q = 0; q + 1 < g.ndig; ++q) {
+        pos -= g.dig[q];
+        out |= ((rest >> pos) & ((1ull << g.dig[q]) - 1)) << shift;
+        shift += g.dig[q];
+    }
+    out |= (uint64_t)k << shift;
+    return (((batch << g.logn) | out) << g.log_r) | rlow;
+}
+}  // namespace gsn
 
 namespace gsn {
 
@@ -32,7 +72,7 @@ __device__ __forceinline__ uint32_t submod(uint32_t a, uint32_t b, uint32_t p) {
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 ntt32_pass(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, const uint2 *__restrict__ wloc,
-           const uint2 *__restrict__ pre_tw, const PassGeom g, const uint32_t p) {
+           const uint2 *__restrict__ pre_tw, const PassGeom32 g, const uint32_t p) {
     extern __shared__ uint32_t tile32[];
     const uint32_t T = 1u << g.log_tile;
     const uint32_t lq = g.log_l;

@@ -91,7 +91,7 @@ template <int A, int B, int C, bool SLOT_FAST, bool PRE, int MIN_BLOCKS>
 __global__ void __launch_bounds__(512, MIN_BLOCKS)
 ntt32_fast_pass(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, const uint2 *__restrict__ tA,
                 const uint2 *__restrict__ tB, const uint2 *__restrict__ t_lo, const uint2 *__restrict__ t_hi,
-                const uint2 *__restrict__ tG, const PassGeom g, const Ntt32Consts c) {
+                const uint2 *__restrict__ tG, const PassGeom32 g, const Ntt32Consts c) {
     using T = FastTile<A, B, C>;
     extern __shared__ uint32_t sm[];
     const uint64_t sub0 = tile_sub0(blockIdx.x, c.slot_shift);

@@ -157,7 +157,7 @@ int get_plan32(gsn_ctx *ctx, uint32_t logn, uint32_t omega, uint32_t mod, int in
 
 template <int A, int B, int C, bool SLOT_FAST, bool PRE>
 int launch_fast32(gsn_ctx *ctx, unsigned grid, cudaStream_t st, const uint32_t *src, uint32_t *dst, const uint2 *tA, const uint2 *tB,
-                  const uint2 *t_lo, const uint2 *t_hi, const uint2 *tG, const gsn::PassGeom &g, const gsn::Ntt32Consts &k) {
+                  const uint2 *t_lo, const uint2 *t_hi, const uint2 *tG, const gsn::PassGeom32 &g, const gsn::Ntt32Consts &k) {
     constexpr int MINB = (A + B + C) == 12 ? 1 : 2;
     auto kern = gsn::ntt32_fast_pass<A, B, C, SLOT_FAST, PRE, MINB>;
     if (!ctx->smem_configured.count((const void *)kern)) {  // function attributes are per device, i.e. per context
@@ -171,7 +171,7 @@ int launch_fast32(gsn_ctx *ctx, unsigned grid, cudaStream_t st, const uint32_t *
 
 template <bool SLOT_FAST, bool PRE>
 int dispatch_fast32(uint32_t L, gsn_ctx *ctx, unsigned grid, cudaStream_t st, const uint32_t *src, uint32_t *dst, const uint2 *tA,
-                    const uint2 *tB, const uint2 *t_lo, const uint2 *t_hi, const uint2 *tG, const gsn::PassGeom &g, const gsn::Ntt32Consts &k) {
+                    const uint2 *tB, const uint2 *t_lo, const uint2 *t_hi, const uint2 *tG, const gsn::PassGeom32 &g, const gsn::Ntt32Consts &k) {
     switch (L) {
         case 8: return launch_fast32<3, 3, 2, SLOT_FAST, PRE>(ctx, grid, st, src, dst, tA, tB, t_lo, t_hi, tG, g, k);
         case 9: return launch_fast32<3, 3, 3, SLOT_FAST, PRE>(ctx, grid, st, src, dst, tA, tB, t_lo, t_hi, tG, g, k);
@@ -185,12 +185,12 @@ int launch_ntt32_fast(gsn_ctx *ctx, Plan32 *pl, uint32_t *d_data, size_t batch, 
     const size_t P = pl->digits.size();
     const uint64_t total = (uint64_t)batch << pl->logn;
     int rc;
-    if ((rc = ensure_work(ctx, total * 4))) return rc;
-    uint32_t *work = (uint32_t *)ctx->work.p;
+    uint32_t *work;
+    if ((rc = ensure_work(ctx, st, total * 4, &work))) return rc;
     uint32_t below = pl->logn;
     for (size_t q = 0; q < P; ++q) {
         below -= pl->digits[q];
-        gsn::PassGeom g;
+        gsn::PassGeom32 g;
         memset(&g, 0, sizeof(g));
         g.log_l = pl->digits[q];
         g.log_s = below;
@@ -224,17 +224,17 @@ int launch_ntt32(gsn_ctx *ctx, Plan32 *pl, uint32_t *d_data, size_t batch, cudaS
     uint32_t v2 = 0;
     while (v2 < (uint32_t)MAX_TILE_LOG32 && !((total >> v2) & 1)) ++v2;
     int rc;
-    if (P > 1 && (rc = ensure_work(ctx, total * 4))) return rc;
-    uint32_t *work = (uint32_t *)ctx->work.p;
+    uint32_t *work = nullptr;
+    if (P > 1 && (rc = ensure_work(ctx, st, total * 4, &work))) return rc;
     auto kern = gsn::ntt32_pass<NTT32_THREADS>;
-    if (!ctx->attr32_set) {
+    if (!ctx->smem_configured.count((const void *)kern)) {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << MAX_TILE_LOG32) * 4));
-        ctx->attr32_set = true;
+        ctx->smem_configured.insert((const void *)kern);
     }
     uint32_t below = pl->logn;
     for (size_t q = 0; q < P; ++q) {
         below -= pl->digits[q];
-        gsn::PassGeom g;
+        gsn::PassGeom32 g;
         memset(&g, 0, sizeof(g));
         g.log_l = pl->digits[q];
         g.log_s = below;

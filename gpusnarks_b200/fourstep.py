@@ -36,7 +36,7 @@ def _ilog2(x):
 
 
 class CudaBackend:
-    """Local transforms through libgpusnarks_b200.so on torch-owned device memory."""
+    """Local transforms through libgpusnarks_b200.so on torch-owned device memory (NCCL-exchange comparison path)."""
 
     def __init__(self, ctx, device):
         self.ctx = ctx
@@ -161,43 +161,101 @@ class _DeviceArray:
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<i4", "data": (int(ptr), False), "version": 3}
 
 
-class FusedFourStepNTT768(FourStepNTT768):
-    """Four-step NTT whose exchange is fused into the transform kernels: the last pass of the
-    column (forward) or row (inverse) transforms stores each output element straight into the
-    destination rank's buffer over NVLink (gsn_ntt768_device_scatter, CUDA-IPC mapped peer
-    memory), so there is no all-to-all and no repacking copy.  NCCL is used only for two
-    stream-ordered barriers per transform (a one-element all-reduce) and for the one-time
-    exchange of the IPC handles.
+# ---- layouts of the fused plan (gsn_fourstep, include/gpusnarks_b200.h)
+def fused_rank_bit(logn, G, max_pass_log=10):
+    """bit of the column index i2 at which the owning rank sits: the top of the low digit of the row transform's
+    first pass (so that every tile of that pass reads one source rank); log2(C) for a one-pass row transform"""
+    log_n2 = logn - split_log_n1(logn)
+    logG = _ilog2(G)
+    npass = -(-log_n2 // max_pass_log) if log_n2 else 1
+    base, extra = divmod(log_n2, npass) if log_n2 else (0, 0)
+    digits = [base + (1 if i < extra else 0) for i in range(npass)]
+    low = sum(digits[1:])
+    if npass < 2 or low < logG:
+        low = log_n2
+    return low - logG
 
-    The plan owns the two buffers: `self.x` (column-block, (n1, C, 24) int32) and `self.y`
-    (row-block, (R, n2, 24)).  forward(): fill self.x, call, read self.y.  inverse(): the reverse.
+
+def to_column_layout(a, logn, G, rank, rank_bit=None):
+    """a: (n, 24) natural order -> this rank's (n1, C, 24) column layout: x[i1][c] = a[i1*n2 + i2(c)], i2(c) = c with the
+    rank inserted at bit rank_bit"""
+    log_n1 = split_log_n1(logn)
+    n1, n2 = 1 << log_n1, 1 << (logn - log_n1)
+    C = n2 // G
+    rb = fused_rank_bit(logn, G) if rank_bit is None else rank_bit
+    v = a.reshape(n1, C >> rb, G, 1 << rb, F.NL)[:, :, rank]
+    return v.reshape(n1, C, F.NL).clone() if torch.is_tensor(a) else np.ascontiguousarray(v.reshape(n1, C, F.NL))
+
+
+def from_column_layouts(blocks, logn, rank_bit=None):
+    """inverse of to_column_layout over all ranks: list of (n1, C, 24) -> (n, 24) natural order"""
+    G = len(blocks)
+    log_n1 = split_log_n1(logn)
+    n1, n2 = 1 << log_n1, 1 << (logn - log_n1)
+    C = n2 // G
+    rb = fused_rank_bit(logn, G) if rank_bit is None else rank_bit
+    out = np.empty((n1, C >> rb, G, 1 << rb, F.NL), dtype=np.uint32)
+    for g, b in enumerate(blocks):
+        out[:, :, g] = np.asarray(b).reshape(n1, C >> rb, 1 << rb, F.NL)
+    return out.reshape(n1 * n2, F.NL)
+
+
+def from_row_layouts(blocks, logn):
+    """list over ranks of (n2, R, 24) row layouts -> (n, 24) natural order: A[(h*R + r) + n1*k2] = y_h[k2][r]"""
+    y = np.stack([np.asarray(b) for b in blocks], axis=1)  # (n2, G, R, 24)
+    return np.ascontiguousarray(y).reshape(-1, F.NL)
+
+
+def to_row_layout(A, logn, G, rank):
+    """A: (n, 24) natural order -> this rank's (n2, R, 24) row layout"""
+    log_n1 = split_log_n1(logn)
+    n1, n2 = 1 << log_n1, 1 << (logn - log_n1)
+    R = n1 // G
+    v = A.reshape(n2, G, R, F.NL)[:, rank]
+    return v.clone() if torch.is_tensor(A) else np.ascontiguousarray(v)
+
+
+class FusedFourStepNTT768:
+    """Four-step NTT whose exchange is fused into the transform kernels (the product path): a thin
+    torch.distributed front end of the C plan object gsn_fourstep.  The last pass of the column
+    transforms stores each output element straight into the destination rank's row buffer over
+    NVLink (CUDA-IPC mapped peer memory), and the first row pass starts, source rank by source rank,
+    as soon as that rank's columns have arrived (arrival flags in peer memory).  torch.distributed
+    is used once, to exchange the IPC handles.
+
+    The plan owns the buffers: `self.x` (column layout, (n1, C, 24) int32) and two row buffers
+    (row layout, (n2, R, 24)); forward(): fill self.x, call, read the returned tensor.
     """
 
-    def __init__(self, ctx, device, logn, omega, group=None, modulus=F.FR, directions=("forward", "inverse"), log_n1=None):
-        super().__init__(CudaBackend(ctx, device), logn, omega, group=group, modulus=modulus, directions=directions, log_n1=log_n1)
-        self.ctx = ctx
-        self.device = device
-        nbytes = self.n1 * self.C * F.NL * 4
-        self._xp = ctx.device_alloc(nbytes)
-        self._yp = ctx.device_alloc(nbytes)
-        self.x = torch.as_tensor(_DeviceArray(self._xp, self.column_block_shape()), device=device)
-        self.y = torch.as_tensor(_DeviceArray(self._yp, self.row_block_shape()), device=device)
-        self._yp2 = ctx.device_alloc(nbytes)  # second receive buffer (forward calls alternate)
-        self.y2 = torch.as_tensor(_DeviceArray(self._yp2, self.row_block_shape()), device=device)
-        self._flip = 1
-        self._timing = {} if os.environ.get("GSN_FOURSTEP_TIMING") else None
-        self._flag = torch.zeros(1, dtype=torch.int32, device=device)
-        # flag array for the peer-memory barrier (8 slots), zeroed before anyone can signal it
-        self._fp = ctx.device_alloc(256)
-        ctx.h2d(self._fp, np.zeros(64, dtype=np.uint32))
-        self._epoch = 0
-        self._nccl_barrier = bool(os.environ.get("GSN_FOURSTEP_NCCL_BARRIER"))
-        self.peers_x, self.peers_y = self._exchange_handles(self._xp), self._exchange_handles(self._yp)
-        self.peers_y2 = self._exchange_handles(self._yp2)
-        self.peer_flags = self._exchange_handles(self._fp)
+    def __init__(self, ctx, device, logn, omega, group=None, modulus=F.FR, directions=("forward", "inverse")):
+        from .ntt import FourStepPlan
+        self.ctx, self.device, self.group = ctx, device, group
+        self.G = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.logn = logn
+        self.plan = FourStepPlan(ctx, logn, omega, self.G, self.rank, directions)
+        self.log_n1, self.log_n2 = self.plan.log_n1, self.plan.log_n2
+        self.n1, self.n2, self.n = 1 << self.log_n1, 1 << self.log_n2, 1 << logn
+        self.C, self.R = self.n2 // self.G, self.n1 // self.G
+        self.rank_bit = self.plan.rank_bit
+        self.x = torch.as_tensor(_DeviceArray(self.plan.x, self.column_block_shape()), device=device)
+        self.y0 = torch.as_tensor(_DeviceArray(self.plan.y0, self.row_block_shape()), device=device)
+        self.y1 = torch.as_tensor(_DeviceArray(self.plan.y1, self.row_block_shape()), device=device)
+        self._cur = self.y0
+        self._imported = []
+        px, py0, py1, pf = (self._exchange_handles(p) for p in (self.plan.x, self.plan.y0, self.plan.y1, self.plan.flags))
         if self.G > 1:
+            self.plan.connect(px, py0, py1, pf)
             dist.barrier(group=self.group)  # every rank has zeroed and published its flags
-        self.logG, self.logC, self.logR = _ilog2(self.G), _ilog2(self.C), _ilog2(self.R)
+
+    def column_block_shape(self):
+        return (self.n1, self.C, F.NL)
+
+    def row_block_shape(self):
+        return (self.n2, self.R, F.NL)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream or 1  # 0 would mean "the context's own stream"
 
     def _exchange_handles(self, ptr):
         if self.G == 1:
@@ -207,79 +265,38 @@ class FusedFourStepNTT768(FourStepNTT768):
         dist.all_gather(allh, mine, group=self.group)
         out = []
         for r, h in enumerate(allh):
-            out.append(ptr if r == self.rank else self.ctx.ipc_import(bytes(h.cpu().numpy().tobytes())))
+            if r == self.rank:
+                out.append(ptr)
+            else:
+                p = self.ctx.ipc_import(bytes(h.cpu().numpy().tobytes()))
+                self._imported.append(p)
+                out.append(p)
         return out
 
-    def _barrier(self):
-        """stream-ordered barrier across the ranks: later kernels on this stream start after every rank got here"""
-        if self.G == 1:
-            return
-        if self._nccl_barrier:
-            dist.all_reduce(self._flag, group=self.group)
-        else:
-            self._epoch += 1
-            self.ctx.peer_barrier(self.peer_flags, self.rank, self._epoch, stream=self.be._stream())
-
     def forward(self, x=None):
-        """column-block self.x -> row-block self.y (returns self.y)"""
+        """column layout self.x -> row layout (returns the row buffer just written)"""
         if x is not None and x.data_ptr() != self.x.data_ptr():
             self.x.copy_(x)
-        be = self.be
-        t = self._timing
-        if t is not None:
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-            ev[0].record()
-        # Receive buffers alternate between calls, so the only hazard left is "stores have landed":
-        # a rank that has passed the barrier of call i+1 knows every rank finished the row pass of
-        # call i, hence its buffer of call i may be overwritten by call i+2 without a second barrier.
-        self._flip ^= 1
-        peers_y, yp, y = (self.peers_y, self._yp, self.y) if self._flip == 0 else (self.peers_y2, self._yp2, self.y2)
-        # column NTTs; output element (k1, c) of this rank goes to rank k1 / R, position [k1 % R][rank*C + c]
-        self.ctx.ntt768_device_scatter(self._xp, self.n1, self.w_col, peers_y, self.rank, rank_shift=self.logR + self.logC,
-                                       ins_shift=self.logC, batch=1, log_r=self.logC, stream=be._stream())
-        if t is not None:
-            ev[1].record()
-        self._barrier()  # all stores into y have landed
-        if t is not None:
-            ev[2].record()
-        be.ntt(y, self.n2, self.R, 0, self.w_row, pre_table=self.tw_fwd)
-        if t is not None:
-            ev[3].record()
-            torch.cuda.synchronize(self.device)
-            for i, name in enumerate(("column+scatter", "barrier", "row")):
-                t[name] = t.get(name, 0.0) + ev[i].elapsed_time(ev[i + 1])
-            t["calls"] = t.get("calls", 0) + 1
-        return y
+        yp = self.plan.forward(self._stream())
+        self._cur = self.y0 if yp == self.plan.y0 else self.y1
+        return self._cur
 
     def inverse(self, y=None):
-        """row-block self.y -> column-block self.x (returns self.x)"""
-        if y is None:
-            y = self.y if self._flip == 0 else self.y2  # the buffer the last forward() filled
-        if y.data_ptr() != self.y.data_ptr():
-            self.y.copy_(y)
-        be = self.be
-        self._barrier()
-        # inverse row NTTs; output element (r, i2) goes to rank i2 / C, position [rank*R + r][i2 % C]
-        self.ctx.ntt768_device_scatter(self._yp, self.n2, self.w_row, self.peers_x, self.rank, rank_shift=self.logC,
-                                       ins_shift=self.logR + self.logC, batch=self.R, log_r=0, inverse_root=True, no_scale=True,
-                                       stream=be._stream())
-        self._barrier()
-        be.ntt(self.x, self.n1, 1, self.logC, self.w_col, inverse_root=True, no_scale=True, pre_table=self.tw_inv)
+        """row layout (the buffer the last forward() filled) -> column layout self.x (returns self.x)"""
+        if y is not None and y.data_ptr() != self._cur.data_ptr():
+            self._cur.copy_(y)
+        self.plan.inverse(self._stream())
         return self.x
+
+    def phase_ms(self):
+        return self.plan.phase_ms()
 
     def close(self):
         torch.cuda.synchronize(self.device)
         if self.G > 1:
             dist.barrier(group=self.group)
-            for r in range(self.G):
-                if r != self.rank:
-                    self.ctx.ipc_close(self.peers_x[r])
-                    self.ctx.ipc_close(self.peers_y[r])
-                    self.ctx.ipc_close(self.peers_y2[r])
-                    self.ctx.ipc_close(self.peer_flags[r])
+            for p in self._imported:
+                self.ctx.ipc_close(p)
             dist.barrier(group=self.group)
-        self.x = self.y = self.y2 = None
-        self.ctx.device_free(self._xp)
-        self.ctx.device_free(self._yp)
-        self.ctx.device_free(self._yp2)
-        self.ctx.device_free(self._fp)
+        self.x = self.y0 = self.y1 = self._cur = None
+        self.plan.close()

@@ -200,7 +200,7 @@ class Context:
 
     def g1_multiexp(self, points, scalars):
         """sum_i scalars[i] * points[i] on MNT4-753 G1 -- the reference's multiexp<mnt4753_G1, Scalar>.  points: (n, 3, 24)
-        projective Montgomery limbs over Fq; scalars: (n, 24) raw integers.  The context field must be FIELD_FQ."""
+        projective Montgomery limbs over Fq; scalars: (n, 24) raw integers.  (Fq is built in: any context field works.)"""
         points = np.ascontiguousarray(points, dtype=np.uint32).reshape(-1, 3, NL)
         scalars = np.ascontiguousarray(scalars, dtype=np.uint32).reshape(-1, NL)
         assert points.shape[0] == scalars.shape[0]
@@ -210,33 +210,31 @@ class Context:
 
     def coset_ntt768(self, a, omega, shift, inverse=False):
         """forward: evaluations of the polynomial with coefficients a on the coset shift * <omega>;
-        inverse: coefficients from such evaluations.  Host arrays in/out (device-resident inside)."""
-        from . import field as F
-        a = np.ascontiguousarray(a, dtype=np.uint32).reshape(-1, NL)
-        n = a.shape[0]
-        d = self.device_alloc(a.nbytes)
-        t = self.device_alloc(a.nbytes)
-        try:
-            self.h2d(d, a)
-            if not inverse:
-                self.fp768_powers_device(t, n, shift)
-                t2 = self.device_alloc(2 * a.nbytes)
-                try:
-                    self.fp768_twiddle_table_device(t2, t, n)
-                    self.ntt768_device_ex(d, n, omega, pre_table=t2)
-                    self.synchronize()
-                finally:
-                    self.device_free(t2)
-            else:
-                self.ntt768_device(d, n, omega, inverse=True)
-                self.fp768_powers_device(t, n, F.mont_inverse(shift))
-                self.fp768_binop_device("mul", d, d, t, n)
-            out = np.empty_like(a)
-            self.d2h(out, d)
-        finally:
-            self.device_free(d)
-            self.device_free(t)
+        inverse: coefficients from such evaluations.  Host arrays in/out (gsn_coset_ntt768_host)."""
+        out = np.ascontiguousarray(a, dtype=np.uint32).reshape(-1, NL).copy()
+        omega, shift = _limbs(omega), _limbs(shift)
+        self._check(self.L.gsn_coset_ntt768_host(self._h, _ptr(out), out.shape[0], _ptr(omega), _ptr(shift), int(bool(inverse))))
         return out
+
+    def coset_ntt768_device(self, dptr, n, omega, shift, inverse=False, batch=1, stream=None):
+        """device-resident coset transform: shift^i fused into the first pass (forward) / n^-1 shift^-i into the last (inverse)"""
+        omega, shift = _limbs(omega), _limbs(shift)
+        self._check(self.L.gsn_coset_ntt768_device(self._h, C.c_void_p(dptr), int(n), int(batch), _ptr(omega), _ptr(shift), int(bool(inverse)),
+                                                   C.c_void_p(stream or 0)))
+
+    # ---- tuning / introspection
+    def set_option(self, option, value):
+        opt = {"flat_table_limit": 1, "plan_cache_bytes": 2, "kernel_variant": 3}[option]
+        self._check(self.L.gsn_ctx_set_option(self._h, opt, C.c_uint64(int(value) & 0xFFFFFFFFFFFFFFFF)))
+
+    def plan_info768(self, n, omega, inverse=False):
+        omega = _limbs(omega)
+        tb, cp, cb = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        passes, two = C.c_uint(), C.c_uint()
+        self._check(self.L.gsn_ntt768_plan_info(self._h, int(n), _ptr(omega), int(bool(inverse)), C.byref(tb), C.byref(passes), C.byref(two),
+                                                C.byref(cp), C.byref(cb)))
+        return {"table_bytes": tb.value, "passes": passes.value, "two_level_boundaries": two.value, "cached_plans": cp.value,
+                "cached_bytes": cb.value}
 
     # ---- 32-bit field
     def best_fft32(self, a, omega, mod, inverse=False):
@@ -265,6 +263,90 @@ class Context:
         self._check(self.L.gsn_int32_issue_rates(self._h, rates, 16, C.byref(nm), C.byref(sm), C.byref(khz)))
         names = ["imad_lo", "imad_hi", "imad_wide", "imad_wide_shared_operands", "imad_wide_x_chain", "iadd3_x_chain"]
         return {"rates": {names[k]: rates[k] for k in range(nm.value)}, "sm_count": sm.value, "sm_clock_khz": khz.value}
+
+
+class FourStepPlan:
+    """gsn_fourstep: one rank's share of a sharded transform (see include/gpusnarks_b200.h)."""
+
+    def __init__(self, ctx, logn, omega, n_ranks, my_rank, directions=("forward", "inverse")):
+        self.ctx = ctx
+        self.L = ctx.L
+        omega = _limbs(omega)
+        d = (1 if "forward" in directions else 0) | (2 if "inverse" in directions else 0)
+        h = C.c_void_p()
+        self._h = None
+        ctx._check(self.L.gsn_fourstep_create(ctx._h, C.byref(h), int(logn), _ptr(omega), int(n_ranks), int(my_rank), d))
+        self._h = h
+        a, b, c, e = C.c_uint(), C.c_uint(), C.c_uint(), C.c_uint()
+        tb = C.c_uint64()
+        ctx._check(self.L.gsn_fourstep_info(h, C.byref(a), C.byref(b), C.byref(c), C.byref(tb), C.byref(e)))
+        self.log_n1, self.log_n2, self.rank_bit, self.table_bytes, self.per_source = a.value, b.value, c.value, tb.value, bool(e.value)
+        px, py0, py1, pf = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        ctx._check(self.L.gsn_fourstep_buffers(h, C.byref(px), C.byref(py0), C.byref(py1), C.byref(pf)))
+        self.x, self.y0, self.y1, self.flags = px.value, py0.value, py1.value, pf.value
+
+    def connect(self, peer_x, peer_y0, peer_y1, peer_flags):
+        def arr(ps):
+            return (C.c_void_p * len(ps))(*[C.c_void_p(p) for p in ps])
+        self.ctx._check(self.L.gsn_fourstep_connect(self._h, arr(peer_x), arr(peer_y0), arr(peer_y1), arr(peer_flags)))
+
+    def forward(self, stream=None):
+        y = C.c_void_p()
+        self.ctx._check(self.L.gsn_fourstep_forward(self._h, C.c_void_p(stream or 0), C.byref(y)))
+        return y.value
+
+    def inverse(self, stream=None):
+        x = C.c_void_p()
+        self.ctx._check(self.L.gsn_fourstep_inverse(self._h, C.c_void_p(stream or 0), C.byref(x)))
+        return x.value
+
+    def phase_ms(self):
+        ms = (C.c_float * 3)()
+        calls = C.c_uint64()
+        self.ctx._check(self.L.gsn_fourstep_phase_ms(self._h, ms, C.byref(calls)))
+        return {"column+scatter": ms[0], "signal": ms[1], "row": ms[2], "calls": calls.value}
+
+    def close(self):
+        if self._h is not None:
+            self.L.gsn_fourstep_destroy(self._h)
+            self._h = None
+
+
+class MultiGpu:
+    """gsn_multi: a sharded transform driven from ONE process over several devices (peer access, no NCCL)."""
+
+    def __init__(self, devices, n, omega, directions=("forward", "inverse")):
+        self.L = _lib.load()
+        omega = _limbs(omega)
+        d = (1 if "forward" in directions else 0) | (2 if "inverse" in directions else 0)
+        h = C.c_void_p()
+        self._h = None
+        devs = (C.c_int * len(devices))(*devices)
+        rc = self.L.gsn_multi_create(C.byref(h), devs, len(devices), int(n), _ptr(omega), d)
+        if rc:
+            raise GsnError(rc, self.L.gsn_last_error().decode())
+        self._h = h
+        self.n = n
+
+    def _check(self, rc):
+        if rc:
+            raise GsnError(rc, self.L.gsn_last_error().decode())
+
+    def ntt_host(self, a, inverse=False):
+        assert a.dtype == np.uint32 and a.flags["C_CONTIGUOUS"] and a.shape == (self.n, NL)
+        self._check(self.L.gsn_multi_ntt768_host(self._h, _ptr(a), int(bool(inverse))))
+        return a
+
+    def ntt_device(self, inverse=False):
+        self._check(self.L.gsn_multi_ntt768_device(self._h, int(bool(inverse))))
+
+    def synchronize(self):
+        self._check(self.L.gsn_multi_synchronize(self._h))
+
+    def close(self):
+        if self._h is not None:
+            self.L.gsn_multi_destroy(self._h)
+            self._h = None
 
 
 def device_count():

@@ -73,6 +73,18 @@ struct Field768 {
         }
         memcpy(r, acc, 96);
     }
+    // r = a^-1 (Fermat: a^(p-2)), Montgomery form in and out; a != 0
+    void inv(uint64_t *r, const uint64_t *a) const {
+        uint64_t e[12], two[12] = {2}, acc[12], base[12];
+        sub_n(e, p, two);
+        memcpy(acc, r1, 96);
+        memcpy(base, a, 96);
+        for (int i = 0; i < 768; ++i) {
+            if ((e[i >> 6] >> (i & 63)) & 1) mul(acc, acc, base);
+            mul(base, base, base);
+        }
+        memcpy(r, acc, 96);
+    }
     // r = a / 2 mod p
     void halve(uint64_t *r, const uint64_t *a) const {
         uint64_t t[13];

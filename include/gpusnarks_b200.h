@@ -54,12 +54,24 @@ typedef struct gsn_ctx gsn_ctx;
 
 /* ---- context: owns a stream, the device workspace and the cached twiddle tables.
  * Replaces the per-call cudaMalloc pair that the reference never frees (fft_kernel.cu:129-134).
- * One context per host thread (calls on one context are serialised by an internal mutex). */
+ * Calls on one context are serialised by an internal mutex; the device-pointer entry points may be used with
+ * several caller streams at once (each stream gets its own scratch buffer). */
 int gsn_ctx_create(gsn_ctx **ctx, int device);
 int gsn_ctx_destroy(gsn_ctx *ctx);
 const char *gsn_last_error(void);
-/* choose the 768-bit modulus for this context's device (default GSN_FIELD_MNT4753_FR) */
+/* choose the 768-bit modulus of THIS context (default GSN_FIELD_MNT4753_FR).  The field constants travel with every
+ * kernel launch as a parameter, so contexts with different fields can share a device, and kernels already enqueued
+ * keep the field they were launched with. */
 int gsn_set_field768(gsn_ctx *ctx, int field);
+/* tuning knobs.  GSN_OPT_FLAT_TABLE_LIMIT (bytes, default 4 GiB): a pass-boundary twiddle table (192 B per element of
+ * the boundary's sub-problem, one product per element) larger than this is replaced by two-level tables of
+ * 2 * sqrt(n) entries and two products per element -- 2^26 needs 3 MB instead of 13 GB.  GSN_OPT_PLAN_CACHE_BYTES
+ * (default 16 GiB, and at most 16 plans): least-recently-used plans are dropped beyond it.  GSN_OPT_KERNEL_VARIANT:
+ * -1 = small-tile kernel only, 0..3 = flag bits of the large-tile kernel (1 wide lazy ranges, 2 twiddle prefetch; default 3). */
+#define GSN_OPT_FLAT_TABLE_LIMIT 1
+#define GSN_OPT_PLAN_CACHE_BYTES 2
+#define GSN_OPT_KERNEL_VARIANT 3
+int gsn_ctx_set_option(gsn_ctx *ctx, int option, uint64_t value);
 /* drop cached plans (twiddle tables) and the workspace */
 int gsn_ctx_trim(gsn_ctx *ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
@@ -83,6 +95,11 @@ int gsn_ntt768_device(gsn_ctx *ctx, uint32_t *d_limbs, size_t n, size_t batch, c
 /* Build (or fetch) the plan for (n, omega, inverse) without running it: twiddle tables are
  * computed on the device once and cached.  Optional; the NTT calls do it on first use. */
 int gsn_ntt768_prepare(gsn_ctx *ctx, size_t n, size_t batch, const uint32_t omega[GSN_FP768_LIMBS], int inverse);
+
+/* Plan of (n, omega, inverse) (built if needed): bytes of twiddle tables it holds, number of passes, how many pass
+ * boundaries use the two-level tables, and the plan cache's population.  Any output pointer may be NULL. */
+int gsn_ntt768_plan_info(gsn_ctx *ctx, size_t n, const uint32_t omega[GSN_FP768_LIMBS], int inverse, uint64_t *table_bytes,
+                         unsigned *passes, unsigned *two_level_boundaries, uint64_t *cached_plans, uint64_t *cached_bytes);
 
 /* Partial transform used by the multi-GPU four-step driver: `d_limbs` holds
  * batch x n x 2^log_r elements indexed (batch | i | r); transforms along i only. */
@@ -109,6 +126,57 @@ int gsn_ntt768_device_scatter(gsn_ctx *ctx, const uint32_t *d_limbs, size_t n, s
                               const uint32_t omega[GSN_FP768_LIMBS], unsigned flags, const uint32_t *d_pre_table,
                               uint32_t *const *peers, unsigned n_peers, unsigned my_rank, unsigned rank_shift,
                               unsigned ins_shift, void *stream);
+/* ---- four-step plan object: one rank's share of a transform of n = 2^logn elements sharded over n_ranks GPUs
+ * (1, 2, 4 or 8), with the exchange fused into the transform kernels (peer stores over NVLink) and the row pass
+ * starting per source rank as its columns arrive (arrival flags in peer memory, no NCCL on the data path).
+ * n = n1 * n2 (n1 = 2^min(10, logn/2)), input index i = i1*n2 + i2, output index k = k1 + n1*k2, C = n2/G, R = n1/G.
+ *   column layout  x[i1][c]  = a[i1*n2 + i2(c)],  i2(c) = c with the rank inserted at bit `rank_bit` (gsn_fourstep_info):
+ *                  the rank's columns come in runs of 2^rank_bit, every G * 2^rank_bit (plain block layout when the
+ *                  row transform is a single pass)                                              shape (n1, C) elements
+ *   row layout     y[k2][r]  = A[(rank*R + r) + n1*k2]                                          shape (n2, R) elements
+ * forward: x -> y (the plan alternates between two y buffers; *y_out receives the one just written);
+ * inverse: y (the buffer of the last forward, or gsn_fourstep_buffers' y0 on a fresh plan) -> x, with omega^-1 and n^-1.
+ * The plan owns its buffers; peers are connected once: in one process by passing the other plans' pointers (with peer
+ * access enabled), across processes through gsn_ipc_export / gsn_ipc_import.  directions: bit 0 forward, bit 1 inverse.
+ * All ranks must issue the same sequence of forward / inverse calls.  Reference structure: the four-step
+ * _basic_parallel_radix2_FFT_inner, test/fft_host.h:56-117. */
+typedef struct gsn_fourstep gsn_fourstep;
+int gsn_fourstep_create(gsn_ctx *ctx, gsn_fourstep **plan, unsigned logn, const uint32_t omega[GSN_FP768_LIMBS], unsigned n_ranks,
+                        unsigned my_rank, unsigned directions);
+int gsn_fourstep_destroy(gsn_fourstep *plan);
+int gsn_fourstep_info(gsn_fourstep *plan, unsigned *log_n1, unsigned *log_n2, unsigned *rank_bit, uint64_t *table_bytes, unsigned *per_source);
+int gsn_fourstep_buffers(gsn_fourstep *plan, void **x, void **y0, void **y1, void **flags);
+int gsn_fourstep_connect(gsn_fourstep *plan, void *const *peer_x, void *const *peer_y0, void *const *peer_y1, void *const *peer_flags);
+int gsn_fourstep_forward(gsn_fourstep *plan, void *stream, void **y_out);
+int gsn_fourstep_inverse(gsn_fourstep *plan, void *stream, void **x_out);
+/* mean milliseconds of the three forward phases (column transforms + scatter, signal/barrier, row transforms); only
+ * collected when the environment variable GSN_FOURSTEP_TIMING is set (it synchronises inside forward) */
+int gsn_fourstep_phase_ms(gsn_fourstep *plan, float ms[3], uint64_t *calls);
+
+/* ---- multi-GPU transform from ONE process: what a C++ caller of best_fft (reference cuda/fft_kernel.h:24-25) reaches
+ * when several devices are visible.  gsn_multi_create builds one context and one four-step plan per device, enables
+ * peer access between them and connects the plans.  gsn_multi_ntt768_host transforms a natural-order host vector in
+ * place (strided copies distribute it in the column layout and collect the row layouts; blocking).
+ * gsn_multi_ntt768_device runs the transform on the plans' device buffers (gsn_multi_device_buffers; asynchronous,
+ * gsn_multi_synchronize waits). */
+typedef struct gsn_multi gsn_multi;
+int gsn_multi_create(gsn_multi **m, const int *devices, unsigned n_devices, size_t n, const uint32_t omega[GSN_FP768_LIMBS], unsigned directions);
+int gsn_multi_destroy(gsn_multi *m);
+int gsn_multi_ntt768_host(gsn_multi *m, uint32_t *limbs, int inverse);
+int gsn_multi_device_buffers(gsn_multi *m, unsigned rank, void **x, void **y);
+int gsn_multi_ntt768_device(gsn_multi *m, int inverse);
+int gsn_multi_synchronize(gsn_multi *m);
+
+/* ---- coset transforms (the prover pipeline iFFT -> coset FFT -> pointwise -> coset iFFT).
+ * forward: evaluations of the polynomial with coefficients a on the coset shift * <omega>: a[i] *= shift^i fused into
+ * the first pass as its pre-twiddle.  inverse: coefficients from such evaluations: omega^-1 transform whose last pass
+ * multiplies output i by n^-1 * shift^-i (post-twiddle), no separate scaling pass.  The shift tables are built once
+ * per (n, shift, direction) from two-level power tables and cached in the context. */
+int gsn_coset_ntt768_device(gsn_ctx *ctx, uint32_t *d_limbs, size_t n, size_t batch, const uint32_t omega[GSN_FP768_LIMBS],
+                            const uint32_t shift[GSN_FP768_LIMBS], int inverse, void *stream);
+int gsn_coset_ntt768_host(gsn_ctx *ctx, uint32_t *limbs, size_t n, const uint32_t omega[GSN_FP768_LIMBS],
+                          const uint32_t shift[GSN_FP768_LIMBS], int inverse);
+
 /* Stream-ordered barrier across the ranks of a four-step transform, in peer memory (no NCCL on the
  * hot path): peer_flags[r] = rank r's array of 8 zero-initialised uint32 slots as mapped in this
  * process.  The kernel publishes `epoch` (must increase by one per call, same on all ranks) with
@@ -152,7 +220,7 @@ int gsn_fp768_inner_product_host(gsn_ctx *ctx, uint32_t out[GSN_FP768_LIMBS], co
 
 /* ---- MNT4-753 G1 multi-exponentiation sum_i s_i * P_i: the reference's multiexp<mnt4753_G1, Scalar>
  * (reference cuda/multi_exp.h:24-25, cuda/multi_exp.cu:104-142; group law cuda/device_field.h:296-437).
- * The context's 768-bit field must be GSN_FIELD_MNT4753_FQ (the curve's base field).  Points are
+ * The curve's base field MNT4-753 Fq is built in: these calls do not depend on gsn_set_field768.  Points are
  * homogeneous projective (X, Y, Z), 3 x 24 limbs each, Montgomery form, identity = any point with Z = 0;
  * scalars are raw 768-bit little-endian integers (the reference reads their bits with hasBitAt).  The result
  * is projective with canonical coordinates.  Algorithm as in the reference: one double-and-add per point,

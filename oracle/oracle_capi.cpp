@@ -2,6 +2,7 @@
 // extern "C" face of the CPU oracle so that tests/ and bench.py (cpu_baseline leg) can
 // drive it through ctypes.  Nothing in gpusnarks_b200/ or include/ may link this.
 #include <omp.h>
+#include <algorithm>
 #include <cstdio>
 #include <chrono>
 #include "field768.h"
@@ -74,6 +75,31 @@ void oracle_dft_points768(uint32_t *out, const uint32_t *limbs, size_t n, const 
 #pragma omp parallel for
     for (size_t i = 0; i < count; ++i) {
         Fp768 z = oracle::dft_point(a, n, Fp768(omega), ks[i]);
+        memcpy(out + i * 24, z.im_rep, 96);
+    }
+}
+
+// The same spot values with every host thread busy: the index range of each Horner evaluation is cut into chunks,
+// chunk c covers j in [j0, j1) and yields P_c = sum_j a[j] x^(j - j0); the value is sum_c P_c x^j0 (x = omega^k).
+// (bench.py's parity leg at 2^24 / 2^26, where one evaluation is 10^7..10^8 products.)
+void oracle_dft_points768_mt(uint32_t *out, const uint32_t *limbs, size_t n, const uint32_t *omega, const uint64_t *ks, size_t count) {
+    const Fp768 *a = reinterpret_cast<const Fp768 *>(limbs);
+    const size_t chunks = std::max<size_t>(1, std::min<size_t>((size_t)omp_get_max_threads() * 4, n / 4096 + 1));
+    const size_t per = (n + chunks - 1) / chunks;
+    std::vector<Fp768> partial(count * chunks, Fp768::zero());
+#pragma omp parallel for collapse(2) schedule(dynamic)
+    for (size_t i = 0; i < count; ++i)
+        for (size_t c = 0; c < chunks; ++c) {
+            const size_t j0 = c * per, j1 = std::min(n, j0 + per);
+            if (j0 >= j1) continue;
+            const Fp768 x = Fp768(omega) ^ ks[i];
+            Fp768 acc = Fp768::zero();
+            for (size_t j = j1; j-- > j0;) acc = acc * x + a[j];
+            partial[i * chunks + c] = acc * (x ^ (uint64_t)j0);
+        }
+    for (size_t i = 0; i < count; ++i) {
+        Fp768 z = Fp768::zero();
+        for (size_t c = 0; c < chunks; ++c) z = z + partial[i * chunks + c];
         memcpy(out + i * 24, z.im_rep, 96);
     }
 }

@@ -39,6 +39,7 @@ def lib():
         L.oracle_ifft768.argtypes = [_u32p, C.c_size_t, _u32p, C.c_int]
         L.oracle_naive_dft768.argtypes = [_u32p, C.c_size_t, _u32p]
         L.oracle_dft_points768.argtypes = [_u32p, _u32p, C.c_size_t, _u32p, _u64p, C.c_size_t]
+        L.oracle_dft_points768_mt.argtypes = [_u32p, _u32p, C.c_size_t, _u32p, _u64p, C.c_size_t]
         L.oracle_fft32.argtypes = [_u32p, C.c_size_t, C.c_uint32, C.c_int]
         L.oracle_ifft32.argtypes = [_u32p, C.c_size_t, C.c_uint32, C.c_int]
         L.oracle_naive_dft32.argtypes = [_u32p, C.c_size_t, C.c_uint32]
@@ -95,6 +96,15 @@ def dft_points768(a, omega, ks):
     ks = np.ascontiguousarray(ks, dtype=np.uint64)
     out = np.empty((len(ks), 24), dtype=np.uint32)
     lib().oracle_dft_points768(out, v, v.shape[0], _c(omega), ks, len(ks))
+    return out
+
+
+def dft_points768_mt(a, omega, ks):
+    """dft_points768 with the index range of every evaluation split over all host threads"""
+    v = _c(a).reshape(-1, 24)
+    ks = np.ascontiguousarray(ks, dtype=np.uint64)
+    out = np.empty((len(ks), 24), dtype=np.uint32)
+    lib().oracle_dft_points768_mt(out, v, v.shape[0], _c(omega), ks, len(ks))
     return out
 
 

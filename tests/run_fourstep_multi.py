@@ -34,6 +34,8 @@ def main():
         got = fourstep.from_row_blocks([b.cpu().numpy().view(np.uint32) for b in blocks], logn)
         ref = ctx.ntt768(a, w)                             # single-GPU transform of the whole vector (itself oracle-checked)
         assert (got == ref).all(), f"rank {rank}: four-step != single-GPU at 2^{logn}"
+        if logn > 20:   # the NCCL comparison path is only run up to 2^20
+            pass
         if logn <= 16 and rank == 0:
             import oracle_lib as O
             assert (got == O.fft768(a, w, 3)).all(), f"four-step != oracle at 2^{logn}"
@@ -41,14 +43,18 @@ def main():
         assert bool((back == x0).all()), f"rank {rank}: inverse(forward) != input at 2^{logn}"
         # fused exchange (peer stores over NVLink) must give the same bits
         fplan = fourstep.FusedFourStepNTT768(ctx, dev, logn, w)
-        fplan.x.copy_(x0)
-        yf = fplan.forward()
-        blocks = [torch.empty_like(yf) for _ in range(world)]
-        dist.all_gather(blocks, yf.contiguous())
-        gotf = fourstep.from_row_blocks([b.cpu().numpy().view(np.uint32) for b in blocks], logn)
-        assert (gotf == ref).all(), f"rank {rank}: fused four-step != single-GPU at 2^{logn}"
-        backf = fplan.inverse()
-        assert bool((backf == x0).all()), f"rank {rank}: fused inverse(forward) != input at 2^{logn}"
+        xf0 = torch.from_numpy(fourstep.to_column_layout(a, logn, world, rank, fplan.rank_bit).view(np.int32)).to(dev)
+        for rep in range(3):   # repeated calls alternate the receive buffers and advance the flag epochs
+            fplan.x.copy_(xf0)
+            yf = fplan.forward()
+            blocks = [torch.empty_like(yf) for _ in range(world)]
+            dist.all_gather(blocks, yf.contiguous())
+            gotf = fourstep.from_row_layouts([b.cpu().numpy().view(np.uint32) for b in blocks], logn)
+            assert (gotf == ref).all(), f"rank {rank}: fused four-step != single-GPU at 2^{logn} (call {rep})"
+            backf = fplan.inverse()
+            assert bool((backf == xf0).all()), f"rank {rank}: fused inverse(forward) != input at 2^{logn} (call {rep})"
+        if rank == 0:
+            print(f"fused 2^{logn}: rank_bit {fplan.rank_bit}, per-source row start {fplan.plan.per_source}, tables {fplan.plan.table_bytes >> 20} MiB", flush=True)
         fplan.close()
         dist.barrier()
     if rank == 0:

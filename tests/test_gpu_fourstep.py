@@ -34,36 +34,15 @@ def test_single_rank_fourstep_vs_oracle(ctx, logn):
     assert bool((back == x0).all())
 
 
-@pytest.mark.parametrize("logn", [6, 12, 16])
-def test_single_rank_fused_fourstep_vs_oracle(ctx, logn):
-    """the scatter-store kernel path with one rank (peer table = the local buffer)"""
-    import torch
-    from gpusnarks_b200 import fourstep
-    dev = torch.device("cuda", 0)
-    n = 1 << logn
-    a = fieldgen.random_elements(n, 177 + logn)
-    w = fieldgen.omega768(n)
-    plan = fourstep.FusedFourStepNTT768(ctx, dev, logn, w)
-    try:
-        x0 = torch.from_numpy(fourstep.to_column_block(a, logn, 1, 0).view(np.int32)).to(dev)
-        plan.x.copy_(x0)
-        y = plan.forward()
-        torch.cuda.synchronize()
-        got = fourstep.from_row_blocks([y.cpu().numpy().view(np.uint32)], logn)
-        assert (got == O.fft768(a, w, 3 if n >= 64 else -1)).all()
-        back = plan.inverse()
-        torch.cuda.synchronize()
-        assert bool((back == x0).all())
-    finally:
-        plan.close()
-
-
 def test_two_rank_fourstep_nccl():
+    """two ranks under torchrun: NCCL all-to-all exchange and the fused plan (peer stores + arrival flags), both against
+    the single-GPU transform and the oracle.  On a one-GPU box the multi-rank product path is still exercised by
+    bench.py --gpus N (which bit-compares with the single-GPU transform) and, with one rank, by test_gpu_round2.py."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29731", os.path.join(ROOT, "tests", "run_fourstep_multi.py"), "14", "20"]
+           "--master-port", "29731", os.path.join(ROOT, "tests", "run_fourstep_multi.py"), "14", "20", "22"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "FOURSTEP_OK" in out.stdout

@@ -69,3 +69,37 @@ def test_device_field_operator_test_compiles(tmp_path):
                            os.path.join(ROOT, "tests", "cpp", "device_field_operator_test.cpp"), "-L" + os.path.join(ROOT, "gpusnarks_b200"),
                            "-lgpusnarks_b200", "-Wl,-rpath," + os.path.join(ROOT, "gpusnarks_b200")])
     assert os.path.exists(exe)
+
+
+def test_large_tile_kernel_index_model(tmp_path):
+    """host replay of the warp-owned 1024-element tile of ntt768_pass2, built from the kernel's own index header
+    (csrc/v2_index.h): ownership, enumeration, unit iterations, bank groups, DFT parity for digit widths 1..10"""
+    exe = str(tmp_path / "test_v2_index")
+    subprocess.check_call([CXX, "-O2", "-std=c++17", "-Wall", "-I" + os.path.join(ROOT, "gpusnarks_b200", "csrc"), "-o", exe,
+                           os.path.join(ROOT, "tests", "cpp", "test_v2_index.cpp")])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "test_v2_index: ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_fused_layout_helpers():
+    """column / row layouts of the fused four-step plan (block-cyclic column ownership, [k2][r] rows) are bijections
+    and agree with the definitions in include/gpusnarks_b200.h"""
+    import numpy as np
+    from gpusnarks_b200 import fourstep as fs
+    for logn, G in [(6, 2), (14, 2), (14, 8), (16, 4), (18, 8)]:
+        n = 1 << logn
+        a = np.arange(n * 24, dtype=np.uint32).reshape(n, 24)
+        log_n1 = fs.split_log_n1(logn)
+        n1, n2 = 1 << log_n1, n >> log_n1
+        C, R, rb = n2 // G, n1 // G, fs.fused_rank_bit(logn, G)
+        cols = [fs.to_column_layout(a, logn, G, r) for r in range(G)]
+        assert (fs.from_column_layouts(cols, logn) == a).all()
+        for g in (0, G - 1):
+            for i1, c in [(0, 0), (1, 1), (n1 - 1, C - 1), (n1 // 2, C // 2 + 1)]:
+                i2 = ((c >> rb) << (rb + G.bit_length() - 1)) | (g << rb) | (c & ((1 << rb) - 1))
+                assert (cols[g][i1, c] == a[i1 * n2 + i2]).all()
+        rows = [fs.to_row_layout(a, logn, G, r) for r in range(G)]
+        assert (fs.from_row_layouts(rows, logn) == a).all()
+        for h in (0, G - 1):
+            for k2, r in [(0, 0), (n2 - 1, R - 1), (n2 // 2, R // 2)]:
+                assert (rows[h][k2, r] == a[(h * R + r) + n1 * k2]).all()

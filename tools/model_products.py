@@ -162,6 +162,51 @@ def shoup_mul(x, w, p):
     return t, val(q)
 
 
+def shoup_mul_3p(x, w, p):
+    """the same product without the final conditional subtraction (`shoup_mul_3p`): t = x*w - q*p for ANY x < 2^768"""
+    X, W, W2, P = limbs(x), limbs(w), limbs((w * R) // p), limbs(p)
+    acc = _Acc(22, NL + 4)
+    for i in range(NL):
+        acc.row(W2, X[i], i, max(0, 22 - i), NL)
+    q = acc.merge(NL + 2)[2:]
+    return (val(mul_lo768(W, X)) - val(mul_lo768(q, P))) % R, val(q)
+
+
+def reduce_small(v, p):
+    """`reduce_small`: v < 1024p -> [0, p) with a quotient estimate from the top limb (q*p by a 24-step mad chain,
+    then two conditional subtractions)"""
+    qmagic = (1 << 32) // ((p >> 736) + 1)
+    q = ((v >> 736) * qmagic) >> 32
+    P, carry, qp = limbs(p), 0, []
+    for i in range(NL):
+        t = P[i] * q + carry
+        qp.append(t & M32)
+        carry = t >> 32
+    assert carry == 0
+    r = (v - val(qp)) % R
+    assert r < 3 * p, "quotient estimate too small"
+    if r >= 2 * p:
+        r -= 2 * p
+    if r >= p:
+        r -= p
+    return r
+
+
+def lazy_pass_bounds(p, stages=10, unit_stages=2):
+    """value bounds inside a pass with wide lazy ranges (fp768.cuh): returns the bound after the last stage in units of
+    p.  unit_stages = 2: warp-owned kernel (stage 1 and half of stage 2 skip the product); 4: CTA-wide kernel
+    (stages 1..4 have unit-twiddle butterflies, which subtract from 3p * 2^(s-1))."""
+    b = 3                      # canonical input (< p) or pre-twiddle product (< 3p)
+    for s in range(1, stages + 1):
+        if s <= unit_stages:   # unit butterflies take t as it is: t < b, subtracted from k p with k = 3 * 2^(s-1)
+            k = 3 << (s - 1)
+            assert b <= k, (s, b, k)
+            b = b + k
+        else:                  # products give t < 3p
+            b = b + 3
+    return b
+
+
 def shoup_constant_from_montgomery(w_mont, p):
     """w'' = floor(w * 2^768 / p) computed the device's way: lo768(w_mont * (-p^-1 mod 2^768))"""
     nprime = (-pow(p, -1, R)) % R
@@ -185,6 +230,18 @@ def self_check(p, cases=400, seed=1):
         assert c < 2 * p and c % p == x * w * rinv % p
         wm = w * R % p
         assert shoup_constant_from_montgomery(wm, p) == (w * R) // p
+        # wide lazy ranges: any x below 2^768 (not only below 2p) gives t in [0, 3p) and t = x*w mod p
+        xs = [R - 1, R - p, 36 * p, 64 * p - 1, rnd.randrange(R), rnd.randrange(36 * p)]
+        xl = xs[it % len(xs)]
+        t3, q3 = shoup_mul_3p(xl, w, p)
+        assert t3 < 3 * p and t3 % p == xl * w % p and 0 <= (xl * w) // p - q3 <= 2
+        worst = max(worst, (xl * w) // p - q3)
+        # reduce_small over its whole domain [0, 1024p)
+        vs = [0, p - 1, p, 2 * p, 3 * p - 1, 36 * p, 66 * p - 1, 1024 * p - 1, rnd.randrange(1024 * p), rnd.randrange(1024) * p,
+              rnd.randrange(1, 1024) * p - 1]
+        vv = vs[it % len(vs)]
+        assert reduce_small(vv, p) == vv % p
+    assert lazy_pass_bounds(p, 10, 2) == 36 and lazy_pass_bounds(p, 10, 4) == 66 and 1024 * p < R
     return worst
 
 
