@@ -6,7 +6,11 @@
 Metric (BASELINE.json): 768-bit NTT butterflies/s, butterflies = (n/2) * log2(n) per transform.
   N = 1   workload = BASELINE.json configs[2]: MNT4-753 Fr forward NTT, n = 2^20, one B200.
   N > 1   workload = configs[3]: MNT4-753 Fr forward NTT, n = 2^24, four-step sharded across
-          the N GPUs with one NCCL all-to-all (strong scaling: the same transform on more GPUs).
+          the N GPUs (strong scaling: the same transform on more GPUs); the exchange is fused into
+          the transform kernels (peer stores over NVLink, arrival flags), gsn_fourstep_*.
+          Outside the timed region the sharded result is compared BIT FOR BIT with the single-GPU
+          transform of the same input on rank 0 and spot-checked against the CPU oracle ("parity");
+          at N = 8 a secondary runs configs[4] (2^26 forward + inverse) the same way.
 A "step" is one whole transform of synthetic random field elements.
   value   device-resident: inputs already in HBM, K steps between barrier + synchronize,
           CUDA events on the launching stream, max over ranks.
@@ -140,6 +144,14 @@ def cpu_reference_run(sample_logn, steps, warmup):
             "seconds_per_step": sec}
 
 
+def spot_check(a_host, omega, got_rows, ks, inverse_of=None):
+    """checker leg: A[k] by Horner on the CPU oracle (all host threads) for the indices ks, against the GPU rows"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    exp = O.dft_points768_mt(a_host, omega, ks)
+    return bool((exp == got_rows).all())
+
+
 def ncu_traffic_bytes(name):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
     summary of one `ncu --set full` capture (profiles/<name>.raw.csv, made by tools/summarize_ncu.py)"""
@@ -203,6 +215,454 @@ def emit(line):
 _REAL_STDOUT = os.dup(1)
 os.dup2(2, 1)  # libraries (e.g. NCCL's version banner) write to fd 1: keep the bench output a single line
 
+DTYPE = "u32x24 (768-bit Montgomery, integer)"
+FIRST_CALL_SCRIPT = r"""
+import json, sys, time
+import numpy as np
+sys.path.insert(0, %r)
+t0 = time.perf_counter()
+import gpusnarks_b200 as g
+from gpusnarks_b200 import field as F
+n = 1 << %d
+a = np.zeros((n, 24), dtype=np.uint32); a[:, 0] = 1234
+w = F.root_of_unity768(n)
+t1 = time.perf_counter()
+ctx = g.Context(0)
+t2 = time.perf_counter()
+ctx.best_fft768(a, w)
+t3 = time.perf_counter()
+ctx.best_fft768(a, w)
+t4 = time.perf_counter()
+print(json.dumps({"import_ms": (t1 - t0) * 1e3, "ctx_create_ms": (t2 - t1) * 1e3, "first_call_ms": (t3 - t2) * 1e3, "second_call_ms": (t4 - t3) * 1e3}))
+"""
+
+
+def peaks_file():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def roofline_block(value, N, logn, ms_step, rates, single, kernels_per_step, kernel_name, table_bytes=None):
+    # roofline denominator: the HIGHEST wide-MAC issue rate the probes reach (distinct-operand, shared-operand
+    # and carry-chain forms all issue at ~32 lanes/clk/SM; taking the maximum is the conservative choice)
+    p_mac = max(rates["rates"][k] for k in ("imad_wide", "imad_wide_shared_operands", "imad_wide_x_chain"))
+    achieved = value * MACS_PER_BUTTERFLY / N  # per GPU
+    n = 1 << logn
+    passes = max(1, -(-logn // 10)) if single else None
+    peaks = peaks_file()
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    # algorithmic bytes per transform: each pass reads and writes every element once (data only)
+    alg_bytes = 2 * passes * n * 96 if single else None
+    return {
+        "kernel": kernel_name,
+        "bound": "int32_mul",
+        "achieved": achieved / 1e12, "peak": p_mac / 1e12, "unit": "T wide-MAC/s (32x32+64 IMAD.WIDE.U32)",
+        "frac": achieved / p_mac,
+        "algorithmic_macs_per_butterfly": MACS_PER_BUTTERFLY,
+        # frac can exceed 1: the 1176-MAC figure is the CIOS product of SURVEY.md 8d, while the kernel multiplies
+        # by table twiddles with a fixed-operand product of 876 wide + 48 low multiplies (= 900 wide-equivalent
+        # issue slots) and skips unit twiddles.  `executed` is the multiplier-pipe utilisation of what really runs
+        # (analytic); the hardware counter (sm__pipe_fmaheavy_cycles_active) is in profiles/ntt768_pass_r02.md.
+        "executed": executed_utilisation(logn, ms_step, p_mac) if single else None,
+        "peak_source": "gsn_int32_issue_rates: max over the IMAD.WIDE.U32 probes (accumulate form with distinct / shared multiplicands, .X carry chains), 8 independent accumulators, measured in this process (SASS-verified loops)",
+        "int32_issue_rates_per_s": rates["rates"],
+        "launches_per_step": kernels_per_step,
+        "avg_launch_ms": (ms_step / kernels_per_step) if kernels_per_step else None,
+        "traffic": ncu_traffic_bytes("ntt768_pass_r02") or ncu_traffic_bytes("ntt768_pass_r01"),
+        "table_bytes": table_bytes,
+        "hbm": {"algorithmic_bytes_per_step": alg_bytes, "achieved_gbs": (alg_bytes / (ms_step * 1e-3) / 1e9) if alg_bytes else None,
+                "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650",
+                "note": "data only (2 x passes x n x 96 B); the pass-boundary twiddle table adds table_bytes of reads per transform"},
+    }
+
+
+def bench_pipeline(ctx, torch, dev, stream, logn, reps=5):
+    """the prover's quotient pipeline, device resident -- iFFT(a), iFFT(b), coset FFT(a), coset
+    FFT(b), pointwise product, coset iFFT: five transforms and one element-wise product per pipeline"""
+    from gpusnarks_b200 import field as F
+    n = 1 << logn
+    w = F.root_of_unity768(n)
+    shift = F.to_mont768(17)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99)
+    a = torch.randint(-(1 << 31), (1 << 31) - 1, (n, 24), dtype=torch.int32, device=dev, generator=gen)
+    b = torch.randint(-(1 << 31), (1 << 31) - 1, (n, 24), dtype=torch.int32, device=dev, generator=gen)
+    a[:, 23] &= 0xFFFF
+    b[:, 23] &= 0xFFFF
+    s = stream.cuda_stream
+
+    def once():
+        for t in (a, b):
+            ctx.ntt768_device(t.data_ptr(), n, w, inverse=True, stream=s)
+            ctx.coset_ntt768_device(t.data_ptr(), n, w, shift, stream=s)
+        ctx.fp768_binop_device("mul", a.data_ptr(), a.data_ptr(), b.data_ptr(), n, stream=s)
+        ctx.coset_ntt768_device(a.data_ptr(), n, w, shift, inverse=True, stream=s)
+    once()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        once()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    return {"workload": f"iFFT x2 -> coset FFT x2 -> pointwise product -> coset iFFT, n=2^{logn}, device resident (gsn_ntt768_device, gsn_coset_ntt768_device, gsn_fp768_binop_device)",
+            "ms_per_pipeline": ms, "transforms_per_pipeline": 5, "butterflies_per_s": 5 * butterflies(logn) / (ms * 1e-3)}
+
+
+def run_single(args, torch, g, F, ctx, dev, stream, logn, config, rates):
+    n = 1 << logn
+    omega = F.root_of_unity768(n)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1)
+    data = torch.randint(-(1 << 31), (1 << 31) - 1, (n, 24), dtype=torch.int32, device=dev, generator=gen)
+    data[:, 23] &= 0xFFFF
+    ctx.prepare768(n, omega)
+    info = ctx.plan_info768(n, omega)
+
+    def step():
+        ctx.ntt768_device(data.data_ptr(), n, omega, stream=stream.cuda_stream)
+    passes = info["passes"]
+    sampler = ClockSampler(dev.index)
+    sampler.start()  # nvidia-smi takes ~0.1 s to start: begin before the warm-up so it is live for the timed region
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize(dev)
+    launches1 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms_step = e0.elapsed_time(e1) / args.steps
+    launches2 = ctx.launch_count()
+
+    # ---- e2e: host-pointer public API, H2D + transform + D2H per step
+    e2e_steps = max(3, min(args.steps, 10))
+    host = torch.empty((n, 24), dtype=torch.int32, pin_memory=True)
+    host.copy_(data)
+    host_np = host.numpy().view(np.uint32)
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize(dev)
+        return (time.perf_counter() - t0) * 1e3 / reps
+    e2e_ms = timed(lambda: ctx.best_fft768(host_np, omega), e2e_steps)
+    # the same steps issued as ONE batch call: copies of consecutive transforms overlap (full-duplex PCIe)
+    hosts = [torch.empty((n, 24), dtype=torch.int32, pin_memory=True) for _ in range(4)]
+    for hbuf in hosts:
+        hbuf.copy_(data)
+    views = [hbuf.numpy().view(np.uint32) for hbuf in hosts]
+    e2e_batched_ms = timed(lambda: ctx.best_fft768_batch(views, omega), 3) / len(views)
+    # the real drop-in signature hands the library PAGEABLE memory (a std::vector): pinned bounce buffers inside
+    pageable = np.array(host_np, copy=True)
+    e2e_pageable_ms = timed(lambda: ctx.best_fft768(pageable, omega), e2e_steps)
+    clocks = sampler.stop()
+
+    bf = butterflies(logn)
+    value = bf / (ms_step * 1e-3)
+    h2d = d2h = n * 96
+    line = {
+        "metric": "768-bit NTT butterflies/s", "value": value, "unit": "butterflies/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": DTYPE, "data": "synthetic", "config": config, "clocks": clocks,
+        "e2e": {"value": bf / (e2e_ms * 1e-3), "unit": "butterflies/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms, "steps": e2e_steps, "api": "gsn_ntt768_host (pinned host buffer)"},
+        "gpu_launches": launches2 - launches1,
+        "roofline": roofline_block(value, 1, logn, ms_step, rates, True, passes, "gsn::ntt768_pass<256,2,false> (CTA-wide) / gsn::ntt768_pass2<1> (warp-owned tiles)",
+                                   info["table_bytes"]),
+        "plan": info,
+        "e2e_batched": {"value": bf / (e2e_batched_ms * 1e-3), "unit": "butterflies/s", "ms_per_step": e2e_batched_ms,
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "api": "gsn_ntt768_host_batch, 4 pinned vectors per call: H2D of vector i+1 overlaps passes and D2H of vector i"},
+        "e2e_pageable": {"value": bf / (e2e_pageable_ms * 1e-3), "unit": "butterflies/s", "ms_per_step": e2e_pageable_ms,
+                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                         "api": "gsn_ntt768_host on pageable memory (what best_fft(std::vector&) passes): pinned bounce buffers + threaded memcpy inside the call"},
+    }
+    secondary = {}
+    try:
+        out = subprocess.run([sys.executable, "-c", FIRST_CALL_SCRIPT % (ROOT, logn)], capture_output=True, text=True, timeout=180)
+        secondary["first_call"] = json.loads(out.stdout.strip().splitlines()[-1])
+        secondary["first_call"]["what"] = f"fresh process: gsn_ctx_create, then the first and second best_fft (2^{logn}, pageable vector); the first call builds the plan"
+    except Exception as e:
+        secondary["first_call"] = {"error": str(e)}
+    try:
+        secondary["pipeline"] = bench_pipeline(ctx, torch, dev, stream, logn)
+    except Exception as e:
+        secondary["pipeline"] = {"error": str(e)}
+    try:
+        secondary["ntt32_cfg2"] = bench_ntt32(ctx, peaks_file().get("hbm_gbs", 6650.0))
+    except Exception as e:
+        secondary["ntt32_cfg2"] = {"error": str(e)}
+    line["secondary"] = secondary
+    try:
+        line["cpu_baseline"] = cpu_reference_run(min(args.cpu_sample_log_n, logn), 1, 0)
+    except Exception as e:  # the bench line must still print
+        line["cpu_baseline"] = {"error": str(e)}
+    emit(line)
+
+
+def gather_to_rank0(torch, dist, t, rank, world):
+    parts = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+    dist.gather(t.contiguous(), parts, dst=0)
+    return parts
+
+
+def sharded_parity(torch, dist, ctx, F, plan, y, logn, omega, rank, world, dev, spot_budget_s=20.0, check_inverse=False):
+    """outside the timed region: rank 0 gathers the shards, runs the SAME input through the single-GPU transform
+    (itself oracle-checked at this size by tests/test_gpu_ntt768.py) and compares every word; then K output indices are
+    evaluated directly by Horner on the CPU oracle (reference harness shape: device result == host result,
+    test/main.cpp:80-84).  Returns (parity dict, single-GPU ms per transform)."""
+    n = 1 << logn
+    G, rb = world, plan.rank_bit
+    n1, n2, C, R = plan.n1, plan.n2, plan.C, plan.R
+    xs = gather_to_rank0(torch, dist, plan.x, rank, world)
+    ys = gather_to_rank0(torch, dist, y, rank, world)
+    res, single_ms = None, None
+    if rank == 0:
+        a = torch.empty((n1, C >> rb, G, 1 << rb, 24), dtype=torch.int32, device=dev)
+        for gidx in range(G):
+            a[:, :, gidx] = xs[gidx].view(n1, C >> rb, 1 << rb, 24)
+        del xs
+        a = a.view(n, 24)
+        got = torch.stack(ys, dim=1).view(n, 24)   # A[(h R + r) + n1 k2] = y_h[k2][r]
+        del ys
+        ref = a.clone()
+        ctx.ntt768_device(ref.data_ptr(), n, omega)
+        ctx.synchronize()
+        same = bool(torch.equal(ref, got))
+        # same-size single-GPU time (device resident), for the scaling figure
+        ms = ctx.time_ntt768(ref.data_ptr(), n, omega, reps=6)
+        single_ms = float(np.median(ms[2:]))
+        del ref
+        # Horner spot checks on the CPU oracle; the number of indices is sized to a time budget
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O
+        O.lib().oracle_set_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1; the other ranks are idle here
+        cal_n = 1 << 16
+        cal = np.ascontiguousarray(a[:cal_n].cpu().numpy().view(np.uint32))
+        t0 = time.perf_counter()
+        O.dft_points768_mt(cal, F.root_of_unity768(cal_n), np.arange(8, dtype=np.uint64))
+        per_spot = (time.perf_counter() - t0) / 8 * (n / cal_n)
+        spots = int(max(2, min(8, spot_budget_s / max(per_spot, 1e-9))))
+        rng = np.random.Generator(np.random.PCG64(2024 + logn))
+        ks = np.unique(np.concatenate([[0, 1, n - 1], rng.integers(0, n, size=spots)]).astype(np.uint64))[:max(spots, 3)]
+        a_host = np.ascontiguousarray(a.cpu().numpy().view(np.uint32))
+        t0 = time.perf_counter()
+        exp = O.dft_points768_mt(a_host, omega, ks)
+        spot_s = time.perf_counter() - t0
+        got_rows = got[torch.from_numpy(ks.astype(np.int64)).to(dev)].cpu().numpy().view(np.uint32)
+        spots_ok = bool((exp == got_rows).all())
+        res = {"vs_single_gpu": same, "elements_compared": n, "spot_checks": int(len(ks)), "spot_checks_ok": spots_ok,
+               "spot_indices": [int(k) for k in ks], "spot_check_seconds": spot_s,
+               "how": "rank 0: gathered shards == gsn_ntt768_device on the gathered input, every word; outputs at spot_indices == Horner evaluation by the CPU oracle (oracle_dft_points768_mt)"}
+        del a, got
+    dist.barrier()
+    return res, single_ms
+
+
+def run_multi(args, torch, dist, g, F, fourstep, ctx, dev, stream, logn, config, rates, rank, world):
+    N = world
+    n = 1 << logn
+    omega = F.root_of_unity768(n)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1 + rank)
+
+    def synth(shape):
+        t = torch.randint(-(1 << 31), (1 << 31) - 1, shape, dtype=torch.int32, device=dev, generator=gen)
+        t[..., 23] &= 0xFFFF
+        return t
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    fused = args.exchange == "fused"
+    if fused:
+        plan = fourstep.FusedFourStepNTT768(ctx, dev, logn, omega, directions=("forward",))
+        plan.x.copy_(synth(plan.column_block_shape()))
+        data = plan.x
+    else:
+        plan = fourstep.FourStepNTT768(fourstep.CudaBackend(ctx, dev), logn, omega, directions=("forward",))
+        data = synth(plan.column_block_shape())
+    state = {}
+
+    def step():
+        state["y"] = plan.forward(data)   # fused: plan.x is only read, a row buffer of the plan receives the result
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    launches1 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches2 = ctx.launch_count()
+
+    # ---- phase split (fused plan): a few extra calls with per-phase events, outside the timed region
+    phases = None
+    if fused:
+        plan.plan.set_timing(True)
+        for _ in range(5):
+            step()
+        barrier()
+        phases = plan.phase_ms()
+        plan.plan.set_timing(False)
+
+    # ---- e2e: pinned shard -> H2D -> forward -> D2H, per rank
+    e2e_steps = max(3, min(args.steps, 10))
+    shard = torch.empty(plan.column_block_shape(), dtype=torch.int32, pin_memory=True)
+    shard.copy_(data)
+    out_host = torch.empty(plan.row_block_shape(), dtype=torch.int32, pin_memory=True)
+    dbuf = data if fused else torch.empty_like(data)
+
+    def e2e_step():
+        dbuf.copy_(shard, non_blocking=True)
+        y = plan.forward(dbuf)
+        out_host.copy_(y, non_blocking=True)
+        torch.cuda.synchronize(dev)
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    clocks = sampler.stop()
+
+    t = torch.tensor([ms_total, e2e_ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+    ms_step = ms_total / args.steps
+    bf = butterflies(logn)
+    value = bf / (ms_step * 1e-3)
+
+    # ---- parity of the sharded result (outside the timed region)
+    parity, single_ms = None, None
+    if fused and not args.no_parity:
+        step()
+        torch.cuda.synchronize(dev)
+        parity, single_ms = sharded_parity(torch, dist, ctx, F, plan, state["y"], logn, omega, rank, world, dev)
+    table_bytes = plan.plan.table_bytes if fused else None
+    per_source = plan.plan.per_source if fused else None
+
+    # ---- configs[4]: 2^26 forward + inverse on 8 GPUs (secondary), same checks plus the round trip
+    cfg5 = None
+    want5 = args.cfg5 == "on" or (args.cfg5 == "auto" and N == 8)
+    if fused and want5:
+        plan.close()
+        ctx.trim()
+        torch.cuda.empty_cache()
+        cfg5 = run_cfg5(args, torch, dist, F, fourstep, ctx, dev, stream, rank, world, synth, barrier)
+
+    if rank == 0:
+        line = {
+            "metric": "768-bit NTT butterflies/s", "value": value, "unit": "butterflies/s", "n_gpus": N, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": DTYPE, "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": bf / (e2e_ms * 1e-3), "unit": "butterflies/s", "h2d_bytes_per_step": data.numel() * 4, "d2h_bytes_per_step": data.numel() * 4,
+                    "ms_per_step": e2e_ms, "steps": e2e_steps, "api": "per rank: pinned shard -> H2D -> gsn_fourstep_forward -> D2H"},
+            "gpu_launches": launches2 - launches1,
+            "roofline": roofline_block(value, N, logn, ms_step, rates, False, None, "gsn::ntt768_pass<256,2,false> + gsn::ntt768_pass2<1> (row pass with arrival flags)", table_bytes),
+            "parity": parity,
+            "phases_ms": phases,
+            "per_source_row_start": per_source,
+            "single_gpu_same_size": ({"ms_per_step": single_ms, "value": bf / (single_ms * 1e-3), "speedup": single_ms / ms_step,
+                                      "efficiency": single_ms / ms_step / N,
+                                      "what": f"the same 2^{logn} transform device resident on rank 0's GPU alone (gsn_ntt768_device), measured in this run"}
+                                     if single_ms else None),
+        }
+        if cfg5 is not None:
+            line["secondary"] = {"cfg5_2pow26_forward_inverse": cfg5}
+        emit(line)
+    ok = True
+    if rank == 0 and parity is not None:
+        ok = parity["vs_single_gpu"] and parity["spot_checks_ok"]
+    if rank == 0 and cfg5 is not None:
+        ok = ok and cfg5["parity"]["vs_single_gpu"] and cfg5["parity"]["spot_checks_ok"] and cfg5["parity"]["round_trip"]
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, src=0)
+    if fused and not want5:
+        plan.close()
+    dist.destroy_process_group()
+    if int(flag[0]) == 0:
+        print("bench.py: PARITY FAILURE (sharded result differs from the single-GPU transform / the oracle)", file=sys.stderr)
+        sys.exit(1)
+
+
+def run_cfg5(args, torch, dist, F, fourstep, ctx, dev, stream, rank, world, synth, barrier):
+    logn = 26
+    n = 1 << logn
+    omega = F.root_of_unity768(n)
+    plan = fourstep.FusedFourStepNTT768(ctx, dev, logn, omega, directions=("forward", "inverse"))
+    x0 = synth(plan.column_block_shape())
+    plan.x.copy_(x0)
+    steps = max(2, min(args.steps, 8))
+
+    def pair():
+        plan.forward()
+        plan.inverse()
+    for _ in range(2):
+        pair()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        pair()
+    e1.record(stream)
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_pair = float(t[0])
+    # every forward + inverse pair must reproduce the input bit for bit, on every rank
+    rt = torch.tensor([1 if bool(torch.equal(plan.x, x0)) else 0], device=dev)
+    dist.all_reduce(rt, op=dist.ReduceOp.MIN)
+    y = plan.forward()
+    torch.cuda.synchronize(dev)
+    parity, single_fwd_ms = sharded_parity(torch, dist, ctx, F, plan, y, logn, omega, rank, world, dev, spot_budget_s=30.0)
+    single_pair_ms = None
+    if rank == 0:
+        # 1-GPU baseline of the same job: 2^26 forward + inverse, device resident (two-level boundary tables)
+        buf = torch.zeros((n, 24), dtype=torch.int32, device=dev)
+        buf[:, 0] = 7
+        ctx.ntt768_device(buf.data_ptr(), n, omega)
+        ctx.ntt768_device(buf.data_ptr(), n, omega, inverse=True)
+        ctx.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(2):
+            ctx.ntt768_device(buf.data_ptr(), n, omega, stream=stream.cuda_stream)
+            ctx.ntt768_device(buf.data_ptr(), n, omega, inverse=True, stream=stream.cuda_stream)
+        ev1.record(stream)
+        torch.cuda.synchronize(dev)
+        single_pair_ms = ev0.elapsed_time(ev1) / 2
+        del buf
+        parity["round_trip"] = bool(int(rt[0]) == 1)
+    dist.barrier()
+    info = {"table_bytes_per_rank": plan.plan.table_bytes, "per_source_row_start": plan.plan.per_source}
+    plan.close()
+    if rank != 0:
+        return None
+    bf2 = 2 * butterflies(logn)
+    return {"workload": f"MNT4-753 Fr forward + inverse NTT (omega^-1, n^-1) n=2^26 on {world}xB200, fused four-step (BASELINE.json configs[4])",
+            "ms_per_pair": ms_pair, "steps": steps, "value": bf2 / (ms_pair * 1e-3), "unit": "butterflies/s",
+            "single_gpu_same_size": {"ms_per_pair": single_pair_ms, "speedup": single_pair_ms / ms_pair, "target": ">= 6x at 8 GPUs",
+                                     "what": "2^26 forward + inverse device resident on rank 0's GPU alone, measured in this run"},
+            "parity": parity, **info}
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -213,7 +673,9 @@ def main():
     ap.add_argument("--log-n", type=int, default=0, help="override the transform size (default 20 at N=1, 24 at N>1)")
     ap.add_argument("--cpu-sample-log-n", type=int, default=20, help="size of the CPU reference sample (2^20 = the whole N=1 workload, ~4 s on 16 cores)")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
-                    help="N>1: fused = last column pass stores into peer memory over NVLink; nccl = all_to_all_single + repack")
+                    help="N>1: fused = gsn_fourstep (peer stores over NVLink + arrival flags); nccl = all_to_all_single + repack (comparison)")
+    ap.add_argument("--no-parity", action="store_true", help="N>1: skip the bit-for-bit comparison with the single-GPU transform")
+    ap.add_argument("--cfg5", default="auto", choices=["auto", "on", "off"], help="N>1: also run 2^26 forward+inverse (auto: at 8 GPUs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -222,8 +684,8 @@ def main():
     logn = args.log_n or (20 if N == 1 else 24)
     workload = (f"MNT4-753 Fr (768-bit) forward NTT n=2^{logn} on 1xB200" if N == 1 else
                 f"MNT4-753 Fr (768-bit) forward NTT n=2^{logn}, four-step sharded across {N}xB200, exchange={args.exchange}"
-                + (" (column-pass epilogue stores tiles into peer HBM over NVLink; NCCL only for two barriers)" if args.exchange == "fused"
-                   else " (NCCL all_to_all_single + repack copy)"))
+                + (" (column-pass epilogue stores tiles into peer HBM over NVLink; row pass starts per source rank on arrival flags; no NCCL on the data path)"
+                   if args.exchange == "fused" else " (NCCL all_to_all_single + repack copy)"))
     config = {"workload": workload, "log_n": logn, "field": "MNT4-753 Fr", "element_bytes": 96,
               "l2": "working set (data + workspace + twiddle table, 3 x n x 96 B) exceeds the 126 MB L2; no flush needed"}
 
@@ -233,9 +695,12 @@ def main():
         sl = min(args.cpu_sample_log_n, logn)
         steps = max(1, min(args.steps, 3))  # bounded: each step is seconds of CPU work
         cb = cpu_reference_run(sl, steps, min(args.warmup, 1))
+        if sl != logn:
+            config = dict(config, cpu_sample=f"the reference's host FFT is timed on a bounded sample of n=2^{sl} and reported as a RATE (butterflies/s); "
+                                             f"the 2^{logn} workload itself is not run on the CPU (it would take minutes per step)")
         line = {"impl": "reference", "metric": "768-bit NTT butterflies/s", "value": cb["value"], "unit": "butterflies/s", "n_gpus": N,
                 "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": cb["seconds_per_step"] * 1e3, "higher_is_better": True,
-                "scaling": "strong" if N > 1 else "weak", "vs_baseline": None, "dtype": "u32x24 (768-bit Montgomery, integer)",
+                "scaling": "strong" if N > 1 else "weak", "vs_baseline": None, "dtype": DTYPE,
                 "data": "synthetic", "config": config, "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "butterflies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
@@ -258,188 +723,11 @@ def main():
     ctx = g.Context(local_rank)
     stream = torch.cuda.Stream(dev)  # a real (non-default) stream: the library launches on it, torch events time it
     torch.cuda.set_stream(stream)
-    n = 1 << logn
-    omega = F.root_of_unity768(n)
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1 + rank)
-
-    def synth(shape):
-        t = torch.randint(-(1 << 31), (1 << 31) - 1, shape, dtype=torch.int32, device=dev, generator=gen)
-        t[..., 23] &= 0xFFFF
-        return t
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
     rates = ctx.int32_issue_rates() if rank == 0 else None
-    launches0 = ctx.launch_count()
-
     if world == 1:
-        data = synth((n, 24))
-        ctx.prepare768(n, omega)
-
-        def step():
-            ctx.ntt768_device(data.data_ptr(), n, omega, stream=stream.cuda_stream)
-        local_bytes = n * 96
-        passes = max(1, -(-logn // 10))
-        kernels_per_step = passes
+        run_single(args, torch, g, F, ctx, dev, stream, logn, config, rates)
     else:
-        if args.exchange == "fused":
-            plan = fourstep.FusedFourStepNTT768(ctx, dev, logn, omega, directions=("forward",))
-            plan.x.copy_(synth(plan.column_block_shape()))
-            data = plan.x
-        else:
-            plan = fourstep.FourStepNTT768(fourstep.CudaBackend(ctx, dev), logn, omega, directions=("forward",))
-            data = synth(plan.column_block_shape())
-        state = {"x": data}
-
-        def step():
-            # forward maps column-block -> row-block (fused: plan.x is only read, plan.y receives the result)
-            state["y"] = plan.forward(state["x"])
-        local_bytes = data.numel() * 4
-        kernels_per_step = None
-
-    sampler = ClockSampler(local_rank)
-    sampler.start()  # nvidia-smi takes ~0.1 s to start: begin before the warm-up so it is live for the timed region
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    launches1 = ctx.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    launches2 = ctx.launch_count()
-
-    # ---- e2e: host-pointer public API, pinned host memory, H2D + transform + D2H per step
-    e2e_steps = max(3, min(args.steps, 10))
-    if world == 1:
-        host = torch.empty((n, 24), dtype=torch.int32, pin_memory=True)
-        host.copy_(data)
-        host_np = host.numpy().view(np.uint32)
-        ctx.best_fft768(host_np, omega)  # warm-up
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            ctx.best_fft768(host_np, omega)
-        barrier()
-        e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-        h2d = d2h = n * 96
-        # the same K steps issued as ONE batch call: copies of consecutive transforms overlap (full-duplex PCIe)
-        hosts = [torch.empty((n, 24), dtype=torch.int32, pin_memory=True) for _ in range(4)]
-        for hbuf in hosts:
-            hbuf.copy_(data)
-        views = [hbuf.numpy().view(np.uint32) for hbuf in hosts]
-        ctx.best_fft768_batch(views, omega)
-        barrier()
-        t0 = time.perf_counter()
-        reps_b = 3
-        for _ in range(reps_b):
-            ctx.best_fft768_batch(views, omega)
-        barrier()
-        e2e_batched_ms = (time.perf_counter() - t0) * 1e3 / (reps_b * len(views))
-    else:
-        shard = torch.empty(plan.column_block_shape(), dtype=torch.int32, pin_memory=True)
-        shard.copy_(data)
-        out_host = torch.empty(plan.row_block_shape(), dtype=torch.int32, pin_memory=True)
-        dbuf = data if args.exchange == "fused" else torch.empty_like(data)
-
-        def e2e_step():
-            dbuf.copy_(shard, non_blocking=True)
-            y = plan.forward(dbuf)
-            out_host.copy_(y, non_blocking=True)
-            torch.cuda.synchronize(dev)
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        barrier()
-        e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-        h2d = d2h = local_bytes
-    clocks = sampler.stop()
-
-    # max over ranks
-    if world > 1:
-        t = torch.tensor([ms_total, e2e_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_ms = float(t[0]), float(t[1])
-    ms_step = ms_total / args.steps
-    bf = butterflies(logn)
-    value = bf / (ms_step * 1e-3)
-
-    if rank == 0:
-        # roofline denominator: the HIGHEST wide-MAC issue rate the probes reach (distinct-operand, shared-operand
-        # and carry-chain forms all issue at ~32 lanes/clk/SM; taking the maximum is the conservative choice)
-        p_mac = max(rates["rates"][k] for k in ("imad_wide", "imad_wide_shared_operands", "imad_wide_x_chain"))
-        achieved = value * MACS_PER_BUTTERFLY / N  # per GPU
-        passes = max(1, -(-logn // 10)) if world == 1 else None
-        peaks = {}
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                peaks = json.load(f)
-        except Exception:
-            pass
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        # algorithmic bytes per transform: each pass reads and writes every element once
-        # (+ one twiddle-table read per pass boundary)
-        if world == 1:
-            alg_bytes = (2 * passes + (passes - 1)) * n * 96
-        else:
-            alg_bytes = None
-        roofline = {
-            "kernel": "gsn::ntt768_pass<256,2>",
-            "bound": "int32_mul",
-            "achieved": achieved / 1e12, "peak": p_mac / 1e12, "unit": "T wide-MAC/s (32x32+64 IMAD.WIDE.U32)",
-            "frac": achieved / p_mac,
-            "algorithmic_macs_per_butterfly": MACS_PER_BUTTERFLY,
-            # frac can exceed 1: the 1176-MAC figure is the CIOS product of SURVEY.md 8d, while the kernel multiplies
-            # by table twiddles with a fixed-operand product of 876 wide + 48 low multiplies (= 900 wide-equivalent
-            # issue slots) and skips unit twiddles.  `executed` is the multiplier-pipe utilisation of what really runs.
-            "executed": executed_utilisation(logn, ms_step, p_mac) if world == 1 else None,
-            "peak_source": "gsn_int32_issue_rates: max over the IMAD.WIDE.U32 probes (accumulate form with distinct / shared multiplicands, .X carry chains), 8 independent accumulators, measured in this process (SASS-verified loops)",
-            "int32_issue_rates_per_s": rates["rates"],
-            "launches_per_step": kernels_per_step,
-            "avg_launch_ms": (ms_step / kernels_per_step) if kernels_per_step else None,
-            "traffic": ncu_traffic_bytes("ntt768_pass_r01"),
-            "hbm": {"algorithmic_bytes_per_step": alg_bytes, "achieved_gbs": (alg_bytes / (ms_step * 1e-3) / 1e9) if alg_bytes else None,
-                    "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650"},
-        }
-        line = {
-            "metric": "768-bit NTT butterflies/s", "value": value, "unit": "butterflies/s", "n_gpus": N, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "strong" if N > 1 else "weak", "vs_baseline": None,
-            "dtype": "u32x24 (768-bit Montgomery, integer)", "data": "synthetic", "config": config, "clocks": clocks,
-            "e2e": {"value": bf / (e2e_ms * 1e-3), "unit": "butterflies/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms, "steps": e2e_steps, "api": "gsn_ntt768_host (pinned host buffer)" if world == 1 else
-                    "pinned shard -> H2D -> FourStepNTT768.forward -> D2H, per rank"},
-            "gpu_launches": launches2 - launches1,
-            "roofline": roofline,
-        }
-        if N == 1:
-            line["e2e_batched"] = {"value": bf / (e2e_batched_ms * 1e-3), "unit": "butterflies/s", "ms_per_step": e2e_batched_ms,
-                                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                                   "api": "gsn_ntt768_host_batch, 4 pinned vectors per call: H2D of vector i+1 overlaps passes and D2H of vector i"}
-            try:
-                line["secondary"] = {"ntt32_cfg2": bench_ntt32(ctx, hbm_peak)}
-            except Exception as e:
-                line["secondary"] = {"error": str(e)}
-            try:
-                line["cpu_baseline"] = cpu_reference_run(min(args.cpu_sample_log_n, logn), 1, 0)
-            except Exception as e:  # the bench line must still print
-                line["cpu_baseline"] = {"error": str(e)}
-        emit(line)
-    if world > 1:
-        tm = getattr(plan, "_timing", None) or getattr(plan, "_timing_nccl", None)
-        if tm and rank == 0:
-            calls = tm.pop("calls", 1)
-            print("phase ms:", {k: round(v / calls, 3) for k, v in tm.items()}, file=sys.stderr)
-        dist.destroy_process_group()
+        run_multi(args, torch, dist, g, F, fourstep, ctx, dev, stream, logn, config, rates, rank, world)
 
 
 if __name__ == "__main__":

@@ -10,13 +10,13 @@ LIB_PATH = os.environ.get("GSN_LIB") or os.path.join(HERE, "libgpusnarks_b200.so
 SYMBOLS = [
     "gsn_ctx_create", "gsn_ctx_destroy", "gsn_last_error", "gsn_set_field768", "gsn_ctx_trim", "gsn_launch_count",
     "gsn_ntt768_host", "gsn_ntt768_host_batch", "gsn_ntt768_device", "gsn_ntt768_prepare", "gsn_ntt768_strided_device",
-    "gsn_ntt768_device_ex", "gsn_fourstep_table768", "gsn_ntt768_device_scatter", "gsn_peer_barrier", "gsn_ipc_export", "gsn_ipc_import", "gsn_ipc_close", "gsn_fp768_binop_host", "gsn_fp768_binop_device", "gsn_fp768_powers_device", "gsn_fp768_twiddle_table_device", "gsn_fp768_inner_product_device", "gsn_fp768_inner_product_host", "gsn_g1_multiexp_host", "gsn_g1_multiexp_device", "gsn_ntt32_host", "gsn_ntt32_device",
+    "gsn_ntt768_device_ex", "gsn_fourstep_table768", "gsn_ntt768_device_scatter", "gsn_peer_barrier", "gsn_ipc_export", "gsn_ipc_import", "gsn_ipc_close", "gsn_fp768_binop_host", "gsn_fp768_binop_device", "gsn_fp768_powers_device", "gsn_fp768_twiddle_table_device", "gsn_fp768_inner_product_device", "gsn_fp768_inner_product_host", "gsn_g1_multiexp_host", "gsn_g1_multiexp_device", "gsn_g1_multiexp_device_ex", "gsn_fp2_binop_host", "gsn_fp2_binop_device", "gsn_ntt32_host", "gsn_ntt32_device",
     "gsn_device_count", "gsn_host_alloc", "gsn_host_free", "gsn_device_alloc", "gsn_device_free",
     "gsn_memcpy_h2d", "gsn_memcpy_d2h", "gsn_ctx_synchronize", "gsn_int32_issue_rates",
     "gsn_ntt768_time_device", "gsn_ntt32_time_device",
     "gsn_ctx_set_option", "gsn_ntt768_plan_info", "gsn_coset_ntt768_device", "gsn_coset_ntt768_host",
     "gsn_fourstep_create", "gsn_fourstep_destroy", "gsn_fourstep_info", "gsn_fourstep_buffers", "gsn_fourstep_connect",
-    "gsn_fourstep_forward", "gsn_fourstep_inverse", "gsn_fourstep_phase_ms",
+    "gsn_fourstep_forward", "gsn_fourstep_inverse", "gsn_fourstep_phase_ms", "gsn_fourstep_set_timing",
     "gsn_multi_create", "gsn_multi_destroy", "gsn_multi_ntt768_host", "gsn_multi_device_buffers", "gsn_multi_ntt768_device",
     "gsn_multi_synchronize",
 ]
@@ -66,6 +66,9 @@ def load():
     L.gsn_fp768_inner_product_host.argtypes = [vp, u32p, u32p, u32p, sz]
     L.gsn_g1_multiexp_host.argtypes = [vp, u32p, u32p, u32p, sz]
     L.gsn_g1_multiexp_device.argtypes = [vp, vp, vp, vp, sz, vp]
+    L.gsn_fp2_binop_host.argtypes = [vp, i, u32p, u32p, u32p, sz]
+    L.gsn_fp2_binop_device.argtypes = [vp, i, vp, vp, vp, sz, vp]
+    L.gsn_g1_multiexp_device_ex.argtypes = [vp, vp, vp, vp, sz, C.c_uint, C.c_uint, vp]
     L.gsn_ntt32_host.argtypes = [vp, u32p, sz, u32, u32, i]
     L.gsn_ntt32_device.argtypes = [vp, vp, sz, sz, u32, u32, i, vp]
     L.gsn_device_count.argtypes = [C.POINTER(i)]
@@ -93,6 +96,7 @@ def load():
     L.gsn_fourstep_forward.argtypes = [vp, vp, C.POINTER(vp)]
     L.gsn_fourstep_inverse.argtypes = [vp, vp, C.POINTER(vp)]
     L.gsn_fourstep_phase_ms.argtypes = [vp, C.POINTER(C.c_float), u64p]
+    L.gsn_fourstep_set_timing.argtypes = [vp, i]
     L.gsn_multi_create.argtypes = [C.POINTER(vp), C.POINTER(i), C.c_uint, sz, u32p, C.c_uint]
     L.gsn_multi_destroy.argtypes = [vp]
     L.gsn_multi_ntt768_host.argtypes = [vp, u32p, i]

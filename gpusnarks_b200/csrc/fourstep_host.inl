@@ -363,7 +363,7 @@ int gsn_fourstep_forward(gsn_fourstep *fs, void *stream, void **y_out) {
     if ((rc = launch_ntt768_range(ctx, pc, (uint32_t *)fs->x.p, 1, fs->logC, ext_flat(nullptr), st, 0, pc->digits.size(), 0, 0, &sc))) return rc;
     if (fs->timing) CU(cudaEventRecord(fs->ev[1], st));
     WaitDesc wd;
-    const bool per_source = fs->per_source && ctx->v2_flags >= 0 && ctx->v2_flags < 4;
+    const bool per_source = fs->per_source;   // the waiting pass always runs on the warp-owned kernel (launch_ntt768_range)
     if (fs->G > 1) {
         if ((rc = fs_signal(fs, st, !per_source))) return rc;   // per-source: signal only, the row pass waits per tile
         if (per_source) {
@@ -417,6 +417,14 @@ int gsn_fourstep_inverse(gsn_fourstep *fs, void *stream, void **x_out) {
     if (fs->G > 1 && (rc = fs_signal(fs, st, true))) return rc;
     if ((rc = launch_ntt768_range(ctx, pc, (uint32_t *)fs->x.p, 1, fs->logC, ext_of(fs->tw_inv), st, 0, pc->digits.size(), 0, 0))) return rc;
     if (x_out) *x_out = fs->x.p;
+    return GSN_OK;
+}
+
+int gsn_fourstep_set_timing(gsn_fourstep *fs, int on) {
+    if (!fs) return fail(GSN_ERR_INVALID_ARG, "null plan");
+    fs->timing = on != 0;
+    fs->phase_calls = 0;
+    for (float &m : fs->phase_ms) m = 0.f;
     return GSN_OK;
 }
 

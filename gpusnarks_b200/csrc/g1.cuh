@@ -9,8 +9,10 @@
 //   s*P  = MSB-first double-and-add    reference mnt4753_G1::operator* (:394-411)
 // What differs: the reference's operator+ has no identity / doubling / inverse cases, so its `zero() + P` is
 // (0,0,0) and every multiple it computes is zero; here the identity is Z == 0 and those cases are handled.
-// The algorithm is the reference's (one scalar multiplication per point, then a tree reduction), not a bucket
-// method: this row is about coverage and bit-exactness, not MSM performance.
+// Two algorithms: the reference's own (one double-and-add per point, then a tree reduction: g1_scalar_mul_kernel +
+// g1_reduce_kernel, kept for very small inputs) and the bucket method (Pippenger) below, which is what a real
+// multi-exponentiation uses: signed c-bit windows, one bucket per (window, |digit|), points sorted by bucket, one thread
+// per bucket, a chunked running-sum reduction per window, and Horner over the window sums on the host (g1_host.h).
 //
 // The Montgomery product is ~1.2k instructions, and the group law calls it 25 times: it is kept out of line
 // (`fq_mul`, operands in local memory) so the kernels stay small enough for the instruction cache.
@@ -185,6 +187,167 @@ __global__ void __launch_bounds__(THREADS) g1_reduce_kernel(uint32_t *out, const
         canonicalize(c_fq, acc.y);
         canonicalize(c_fq, acc.z);
         g1_store(out, acc);
+    }
+}
+
+// ------------------------------------------------------------------ Fq2 = Fq[u] / (u^2 - 13)
+// The reference's `fp2` (cuda/device_field.h:220-294): elements x + y u stored as (x, y), 2 x 24 limbs, Montgomery
+// form; product by Karatsuba, aA + 13 bB and (a + b)(A + B) - aA - bB (device_field.h:253-262).  The reference multiplies
+// by the raw integer 13 through its Montgomery routine (which scales by R^-1); here 13 bB is the field multiple, formed
+// by additions (13 = 8 + 4 + 1).  op: 0 mul, 1 add, 2 sub; canonical outputs.
+__global__ void fp2_binop768(uint32_t *out, const uint32_t *a, const uint32_t *b, uint64_t count, int op) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint32_t ax[NL], ay[NL], bx[NL], by[NL], rx[NL], ry[NL];
+    load_elem(ax, a + i * 2 * NL);
+    load_elem(ay, a + i * 2 * NL + NL);
+    load_elem(bx, b + i * 2 * NL);
+    load_elem(by, b + i * 2 * NL + NL);
+    if (op == 1) { fq_add(rx, ax, bx); fq_add(ry, ay, by); }
+    else if (op == 2) { fq_sub(rx, ax, bx); fq_sub(ry, ay, by); }
+    else {
+        uint32_t aA[NL], bB[NL], s1[NL], s2[NL], t[NL], t4[NL];
+        fq_mul(aA, ax, bx);
+        fq_mul(bB, ay, by);
+        fq_add(s1, ax, ay);
+        fq_add(s2, bx, by);
+        fq_mul(ry, s1, s2);
+        fq_sub(ry, ry, aA);
+        fq_sub(ry, ry, bB);
+        fq_add(t, bB, bB);        // 2 bB
+        fq_add(t4, t, t);         // 4 bB
+        fq_add(t, t4, t4);        // 8 bB
+        fq_add(t, t, t4);         // 12 bB
+        fq_add(t, t, bB);         // 13 bB
+        fq_add(rx, aA, t);
+    }
+    canonicalize(c_fq, rx);
+    canonicalize(c_fq, ry);
+    store_elem(out + i * 2 * NL, rx);
+    store_elem(out + i * 2 * NL + NL, ry);
+}
+
+// ------------------------------------------------------------------ bucket method (Pippenger)
+// Signed window digits of the raw 768-bit scalars.  Window w covers bits [w c, (w+1) c); with the carry of the previous
+// window v = bits + carry, and v > 2^(c-1) is recoded as v - 2^c with a carry into the next window, so |digit| <= 2^(c-1).
+// keys[w * n + i] = w * bs + |digit|, bs = 2^(c-1) + 1 buckets per window (|digit| = 0: nothing to add, bucket 0 is ignored),
+// vals[w * n + i] = 2 i + (digit < 0).
+__global__ void g1_digits_kernel(uint32_t *keys, uint32_t *vals, const uint32_t *scalars, uint64_t n, uint32_t c, uint32_t windows, uint32_t bs) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t k[NL + 1];
+    load_elem(k, scalars + i * NL);
+    k[NL] = 0;
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < windows; ++w) {
+        const uint32_t bit = w * c, word = bit >> 5, off = bit & 31;
+        uint32_t v = 0;
+        if (word <= NL - 1) {
+            const uint64_t two = (uint64_t)k[word] | ((uint64_t)k[word + 1] << 32);
+            v = (uint32_t)(two >> off) & ((1u << c) - 1);
+        }
+        v += carry;
+        uint32_t neg = 0;
+        carry = 0;
+        if (v > (1u << (c - 1))) { v = (1u << c) - v; neg = 1; carry = 1; }
+        keys[(uint64_t)w * n + i] = w * bs + v;       // v <= 2^(c-1)
+        vals[(uint64_t)w * n + i] = (uint32_t)(2 * i + neg);
+    }
+}
+
+// first index of the sorted key array that is >= key
+__device__ __forceinline__ uint64_t g1_lower_bound(const uint32_t *keys, uint64_t count, uint32_t key) {
+    uint64_t lo = 0, hi = count;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (keys[mid] < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// one thread per (window, bucket): buckets[key] = sum of the (signed) points whose sorted key equals `key`
+__global__ void __launch_bounds__(128) g1_bucket_kernel(uint32_t *buckets, const uint32_t *points, const uint32_t *keys, const uint32_t *vals,
+                                                        uint64_t pairs, uint32_t nbuckets, uint32_t bs) {
+    const uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
+    if (key >= nbuckets) return;
+    G1 acc, P, t;
+    g1_set_identity(acc);
+    if (key % bs != 0) {
+        uint64_t lo = g1_lower_bound(keys, pairs, key);
+        for (; lo < pairs && keys[lo] == key; ++lo) {
+            const uint32_t v = vals[lo];
+            g1_load(P, points + (uint64_t)(v >> 1) * 3 * NL);
+            if (v & 1) {  // -P = (X, -Y, Z); lazy values: 2p - Y stays in [0, 2p]... use the field subtraction from zero
+                uint32_t zero[NL];
+                for (int i = 0; i < NL; ++i) zero[i] = 0;
+                fq_sub(P.y, zero, P.y);
+            }
+            g1_add(t, acc, P);
+            g1_copy(acc, t);
+        }
+    }
+    g1_store(buckets + (uint64_t)key * 3 * NL, acc);
+}
+
+// small multiple k * P by double-and-add (k < 2^16)
+__device__ __noinline__ void g1_mul_small(G1 &r, const G1 &p, uint32_t k) {
+    G1 acc, t;
+    g1_set_identity(acc);
+    for (int bit = 31 - __clz(k | 1); bit >= 0; --bit) {
+        g1_dbl(t, acc);
+        if ((k >> bit) & 1) g1_add(acc, t, p);
+        else g1_copy(acc, t);
+    }
+    g1_copy(r, acc);
+}
+
+// one block per window: S_w = sum_{b=1}^{nb} b * B[w][b], nb = 2^(c-1).  Thread t takes the buckets
+// (t m, (t+1) m], m = nb / THREADS: a descending running sum gives sum (b - t m) B_b and the chunk total T_t, the chunk
+// contributes that plus (t m) * T_t; the THREADS contributions are added by a shared-memory tree.  Canonical output.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) g1_window_reduce_kernel(uint32_t *out, const uint32_t *buckets, uint32_t c, uint32_t bs) {
+    extern __shared__ uint32_t g1_red[];  // THREADS * 72 words
+    const uint32_t w = blockIdx.x, nb = 1u << (c - 1);
+    const uint32_t T = nb < (uint32_t)THREADS ? nb : (uint32_t)THREADS, m = nb / T;
+    const uint32_t *B = buckets + (uint64_t)w * bs * 3 * NL;
+    G1 run, sum, t, nxt;
+    g1_set_identity(run);
+    g1_set_identity(sum);
+    if (threadIdx.x < T) {
+        const uint32_t b0 = threadIdx.x * m;
+        for (uint32_t b = b0 + m; b > b0; --b) {
+            g1_load(nxt, B + (uint64_t)b * 3 * NL);
+            g1_add(t, run, nxt);
+            g1_copy(run, t);
+            g1_add(t, sum, run);
+            g1_copy(sum, t);
+        }
+        if (b0) {
+            g1_mul_small(nxt, run, b0);
+            g1_add(t, sum, nxt);
+            g1_copy(sum, t);
+        }
+    }
+    uint32_t *mine = g1_red + threadIdx.x * 3 * NL;
+    for (int i = 0; i < NL; ++i) { mine[i] = sum.x[i]; mine[NL + i] = sum.y[i]; mine[2 * NL + i] = sum.z[i]; }
+    __syncthreads();
+    for (int half = THREADS / 2; half >= 1; half >>= 1) {
+        if ((int)threadIdx.x < half) {
+            const uint32_t *o = g1_red + (threadIdx.x + half) * 3 * NL;
+            for (int i = 0; i < NL; ++i) { sum.x[i] = mine[i]; sum.y[i] = mine[NL + i]; sum.z[i] = mine[2 * NL + i]; }
+            for (int i = 0; i < NL; ++i) { nxt.x[i] = o[i]; nxt.y[i] = o[NL + i]; nxt.z[i] = o[2 * NL + i]; }
+            g1_add(t, sum, nxt);
+            for (int i = 0; i < NL; ++i) { mine[i] = t.x[i]; mine[NL + i] = t.y[i]; mine[2 * NL + i] = t.z[i]; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NL; ++i) { sum.x[i] = mine[i]; sum.y[i] = mine[NL + i]; sum.z[i] = mine[2 * NL + i]; }
+        canonicalize(c_fq, sum.x);
+        canonicalize(c_fq, sum.y);
+        canonicalize(c_fq, sum.z);
+        g1_store(out + (uint64_t)w * 3 * NL, sum);
     }
 }
 

@@ -7,6 +7,7 @@
 // There is no CPU fallback: without a CUDA device every entry point fails with
 // GSN_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
 #include <cstdarg>
@@ -24,6 +25,7 @@
 #include "../../include/gsn_constants.h"
 #include "fp768.cuh"
 #include "g1.cuh"
+#include "../../include/fields/g1_host.h"
 #include "../../include/fields/fp768_host.h"
 #include "microbench.cuh"
 #include "ntt32.cuh"
@@ -139,7 +141,7 @@ struct gsn_ctx {
     size_t flat_table_limit = (size_t)4 << 30;   // a pre-twiddle table larger than this becomes two-level
     size_t plan_cache_bytes = (size_t)16 << 30;  // least-recently-used 768-bit plans are dropped beyond this (and beyond 16 plans)
     uint64_t use_clock = 0;
-    int v2_flags = gsn::V2_LAZY | gsn::V2_PREFETCH;  // large-tile kernel variant; -1 = always the small-tile kernel
+    int v2_flags = 4;  // kernel for 1024-element tiles: 4 / -1 = CTA-wide, 1 = warp-owned tiles (lazy ranges), 3 = + prefetch
     uint64_t launches = 0;
     int sm_count = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -451,11 +453,12 @@ int launch_ntt768_range(gsn_ctx *ctx, Plan768 *pl, uint32_t *d_data, size_t batc
     gsn::ScatterDesc no_scatter;
     memset(&no_scatter, 0, sizeof(no_scatter));
 
-    // kernel variant: 0..3 = warp-owned large-tile kernel (flag bits: 1 lazy ranges, 2 prefetch) for 1024-element tiles;
-    // 4 (or -1) = CTA-wide kernel, strict ranges; 5 = CTA-wide kernel, wide lazy ranges.  Smaller tiles always CTA-wide.
+    // kernel variant for 1024-element tiles: 1 / 3 = warp-owned tiles with wide lazy ranges (3: + twiddle prefetch),
+    // 4 (or -1) = CTA-wide kernel.  Smaller tiles always use the CTA-wide kernel.  (Measured on B200 at 2^20: CTA-wide
+    // 1.281 ms, warp-owned lazy 1.297 ms, + prefetch 1.337 ms; strict-range warp-owned 1.408 ms and a lazy CTA-wide
+    // kernel 1.308 ms were built, measured and removed -- profiles/variants_r02.jsonl.)
     const int variant = ctx->v2_flags < 0 ? 4 : ctx->v2_flags;
-    const bool cta_lazy = variant == 5;
-    auto kern = cta_lazy ? gsn::ntt768_pass<NTT768_THREADS, 2, true> : gsn::ntt768_pass<NTT768_THREADS, 2, false>;
+    auto kern = gsn::ntt768_pass<NTT768_THREADS, 2>;
     if (!ctx->smem_configured.count((const void *)kern)) {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << MAX_PASS_LOG) * gsn::SMEM_PITCH4 * 16));
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -531,13 +534,9 @@ int launch_ntt768_range(gsn_ctx *ctx, Plan768 *pl, uint32_t *d_data, size_t batc
         const unsigned grid = (unsigned)(ntiles ? ntiles : (total >> log_tile));
         const gsn::ScatterDesc &sc = (scatter && q + 1 == P) ? *scatter : no_scatter;
         const uint32_t *wloc = (const uint32_t *)pl->wloc.p;
-        if (log_tile == 10 && g.log_l >= 1 && variant < 4) {
-            switch (variant) {
-                case 0: rc = launch_pass2<0>(ctx, grid, smem, st, src, dst, wloc, g, pd, post, sc); break;
-                case 1: rc = launch_pass2<1>(ctx, grid, smem, st, src, dst, wloc, g, pd, post, sc); break;
-                case 2: rc = launch_pass2<2>(ctx, grid, smem, st, src, dst, wloc, g, pd, post, sc); break;
-                default: rc = launch_pass2<3>(ctx, grid, smem, st, src, dst, wloc, g, pd, post, sc); break;
-            }
+        if (log_tile == 10 && g.log_l >= 1 && (variant < 4 || g.wait_flags)) {   // a pass that waits on arrival flags needs the warp-owned kernel
+            if (variant == 3) rc = launch_pass2<3>(ctx, grid, smem, st, src, dst, wloc, g, pd, post, sc);
+            else rc = launch_pass2<1>(ctx, grid, smem, st, src, dst, wloc, g, pd, post, sc);
             if (rc) return rc;
         } else {
             if (g.wait_flags) return fail(GSN_ERR_INVALID_ARG, "arrival flags need the large-tile kernel");
@@ -605,7 +604,7 @@ int gsn_ctx_create(gsn_ctx **out, int device) {
     for (int d = 0; d < 2; ++d) CU(cudaEventCreateWithFlags(&ctx->ev_io_free[d], cudaEventDisableTiming));
     int rc = set_field(ctx.get(), GSN_FIELD_MNT4753_FR);
     if (rc) return rc;
-    if (const char *v = getenv("GSN_NTT768_VARIANT")) ctx->v2_flags = atoi(v);           // -1 small-tile kernel only, 0..3 flags of ntt768_pass2
+    if (const char *v = getenv("GSN_NTT768_VARIANT")) { const int k = atoi(v); if (k == -1 || k == 1 || k == 3 || k == 4) ctx->v2_flags = k; }
     if (const char *v = getenv("GSN_FLAT_TABLE_LIMIT")) ctx->flat_table_limit = strtoull(v, nullptr, 10);
     *out = ctx.release();
     return GSN_OK;
@@ -671,7 +670,7 @@ int gsn_ctx_set_option(gsn_ctx *ctx, int option, uint64_t value) {
             evict_plans768(ctx, nullptr);
             break;
         case GSN_OPT_KERNEL_VARIANT:
-            if ((int64_t)value < -1 || (int64_t)value > 5) return fail(GSN_ERR_INVALID_ARG, "kernel variant %lld", (long long)value);
+            if ((int64_t)value != -1 && value != 1 && value != 3 && value != 4) return fail(GSN_ERR_INVALID_ARG, "kernel variant %lld (1, 3, 4 or -1)", (long long)value);
             ctx->v2_flags = (int)(int64_t)value;
             break;
         default: return fail(GSN_ERR_INVALID_ARG, "unknown option %d", option);
@@ -1000,11 +999,8 @@ int gsn_fp768_inner_product_host(gsn_ctx *ctx, uint32_t *out, const uint32_t *a,
     return GSN_OK;
 }
 
-int gsn_g1_multiexp_device(gsn_ctx *ctx, uint32_t *d_out, const uint32_t *d_points, const uint32_t *d_scalars, size_t n, void *stream) {
-    if (!ctx || !d_out || !d_points || !d_scalars) return fail(GSN_ERR_INVALID_ARG, "null argument");
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+// the reference's own algorithm: one double-and-add per point, then a tree reduction (tiny inputs, and the A/B of the tests)
+static int g1_multiexp_naive(gsn_ctx *ctx, uint32_t *d_out, const uint32_t *d_points, const uint32_t *d_scalars, size_t n, cudaStream_t st) {
     int rc;
     uint32_t *work;
     if ((rc = ensure_work(ctx, st, std::max<size_t>(n, 1) * 288, &work))) return rc;
@@ -1021,6 +1017,102 @@ int gsn_g1_multiexp_device(gsn_ctx *ctx, uint32_t *d_out, const uint32_t *d_poin
     red<<<1, RT, RT * 288, st>>>(d_out, work, n);
     ctx->launches++;
     CU(cudaGetLastError());
+    return GSN_OK;
+}
+
+// bucket method: signed c-bit windows -> (bucket, point) pairs sorted by bucket (CUB radix sort) -> one thread per
+// bucket -> per-window running-sum reduction -> Horner over the window sums on the host (g1_host.h).  Blocking.
+static int g1_multiexp_pippenger(gsn_ctx *ctx, uint32_t *d_out, const uint32_t *d_points, const uint32_t *d_scalars, size_t n, cudaStream_t st,
+                                 unsigned c_override) {
+    int rc;
+    uint32_t c = c_override ? c_override : (uint32_t)std::min<int>(16, std::max<int>(2, (int)ilog2(n) - 3));
+    const uint32_t windows = (768 + 1 + c - 1) / c, nb = 1u << (c - 1), bs = nb + 1;
+    const uint64_t pairs = (uint64_t)n * windows, nbuckets = (uint64_t)windows * bs;
+    if (pairs >= (1ull << 31)) return fail(GSN_ERR_TOO_LARGE, "multiexp of %zu points: %llu (point, window) pairs", n, (unsigned long long)pairs);
+    DevBuf keys, vals, keys2, vals2, tmp, buckets, wsum;
+    if ((rc = dev_alloc(keys, pairs * 4)) || (rc = dev_alloc(vals, pairs * 4)) || (rc = dev_alloc(keys2, pairs * 4)) || (rc = dev_alloc(vals2, pairs * 4)) ||
+        (rc = dev_alloc(buckets, nbuckets * 288)) || (rc = dev_alloc(wsum, (size_t)windows * 288))) return rc;
+    gsn::g1_digits_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((uint32_t *)keys.p, (uint32_t *)vals.p, d_scalars, n, c, windows, bs);
+    int key_bits = 1;
+    while ((1ull << key_bits) < nbuckets) ++key_bits;
+    size_t tmp_bytes = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t *)keys.p, (uint32_t *)keys2.p, (const uint32_t *)vals.p, (uint32_t *)vals2.p,
+                                       (int)pairs, 0, key_bits, st));
+    if ((rc = dev_alloc(tmp, std::max<size_t>(tmp_bytes, 16)))) return rc;
+    CU(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, (const uint32_t *)keys.p, (uint32_t *)keys2.p, (const uint32_t *)vals.p, (uint32_t *)vals2.p,
+                                       (int)pairs, 0, key_bits, st));
+    gsn::g1_bucket_kernel<<<(unsigned)((nbuckets + 127) / 128), 128, 0, st>>>((uint32_t *)buckets.p, d_points, (const uint32_t *)keys2.p,
+                                                                              (const uint32_t *)vals2.p, pairs, (uint32_t)nbuckets, bs);
+    constexpr int WT = 64;
+    auto red = gsn::g1_window_reduce_kernel<WT>;
+    if (!ctx->smem_configured.count((const void *)red)) {
+        CU(cudaFuncSetAttribute(red, cudaFuncAttributeMaxDynamicSharedMemorySize, WT * 288));
+        ctx->smem_configured.insert((const void *)red);
+    }
+    red<<<windows, WT, WT * 288, st>>>((uint32_t *)wsum.p, (const uint32_t *)buckets.p, c, bs);
+    ctx->launches += 3;
+    CU(cudaGetLastError());
+    std::vector<gsn::host::G1Host> S(windows);
+    static_assert(sizeof(gsn::host::G1Host) == 288, "three 96-byte coordinates");
+    CU(cudaMemcpyAsync(S.data(), wsum.p, (size_t)windows * 288, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    // Horner over the windows, most significant first: acc = 2^c acc + S_w
+    gsn::host::G1Ops ops(gsn::host::fq_field());
+    gsn::host::G1Host acc;
+    ops.identity(acc);
+    for (uint32_t w = windows; w-- > 0;) {
+        if (!ops.is_identity(acc))
+            for (uint32_t k = 0; k < c; ++k) ops.dbl(acc, acc);
+        ops.add(acc, acc, S[w]);
+    }
+    CU(cudaMemcpyAsync(d_out, &acc, 288, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    return GSN_OK;
+}
+
+int gsn_g1_multiexp_device_ex(gsn_ctx *ctx, uint32_t *d_out, const uint32_t *d_points, const uint32_t *d_scalars, size_t n, unsigned method,
+                              unsigned window_bits, void *stream) {
+    if (!ctx || !d_out || !d_points || !d_scalars) return fail(GSN_ERR_INVALID_ARG, "null argument");
+    if (method > 2 || window_bits > 16 || window_bits == 1) return fail(GSN_ERR_INVALID_ARG, "method %u, window_bits %u", method, window_bits);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    if (method == 1 || (method == 0 && n < 8)) return g1_multiexp_naive(ctx, d_out, d_points, d_scalars, n, st);
+    return g1_multiexp_pippenger(ctx, d_out, d_points, d_scalars, n, st, window_bits);
+}
+
+int gsn_g1_multiexp_device(gsn_ctx *ctx, uint32_t *d_out, const uint32_t *d_points, const uint32_t *d_scalars, size_t n, void *stream) {
+    return gsn_g1_multiexp_device_ex(ctx, d_out, d_points, d_scalars, n, 0, 0, stream);
+}
+
+int gsn_fp2_binop_device(gsn_ctx *ctx, int op, uint32_t *d_out, const uint32_t *d_a, const uint32_t *d_b, size_t count, void *stream) {
+    if (!ctx || !d_out || !d_a || !d_b) return fail(GSN_ERR_INVALID_ARG, "null argument");
+    if (op < 0 || op > 2) return fail(GSN_ERR_INVALID_ARG, "op %d", op);
+    if (count == 0) return GSN_OK;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    gsn::fp2_binop768<<<(unsigned)((count + 63) / 64), 64, 0, stream ? (cudaStream_t)stream : ctx->stream>>>(d_out, d_a, d_b, count, op);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return GSN_OK;
+}
+
+int gsn_fp2_binop_host(gsn_ctx *ctx, int op, uint32_t *out, const uint32_t *a, const uint32_t *b, size_t count) {
+    if (!ctx || !out || !a || !b) return fail(GSN_ERR_INVALID_ARG, "null argument");
+    if (count == 0) return GSN_OK;
+    DevBuf da, db, dc;
+    int rc;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        CU(cudaSetDevice(ctx->device));
+        if ((rc = dev_alloc(da, count * 192)) || (rc = dev_alloc(db, count * 192)) || (rc = dev_alloc(dc, count * 192))) return rc;
+        CU(cudaMemcpyAsync(da.p, a, count * 192, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(db.p, b, count * 192, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if ((rc = gsn_fp2_binop_device(ctx, op, (uint32_t *)dc.p, (const uint32_t *)da.p, (const uint32_t *)db.p, count, nullptr))) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaMemcpyAsync(out, dc.p, count * 192, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return GSN_OK;
 }
 

@@ -176,12 +176,10 @@ __device__ __forceinline__ void sts_elem(uint4 *s, const uint32_t *r) {
 }
 
 // ------------------------------------------------------------------ CTA-wide kernel (any tile size)
-// CTA-wide enumeration of the butterflies of every stage, one __syncthreads per stage.  Stages 2..4 are enumerated
-// twiddle-major, so the butterflies with a unit twiddle fill whole warps and skip the product (1.875 of 10 stages' worth).
-// LZ = wide lazy ranges (fp768.cuh): no conditional subtractions inside the pass.  A unit butterfly of stage s takes t
-// as it is (< 3p 2^(s-1)) and subtracts from 3p 2^(s-1); bounds: < 6p, 12p, 24p, 48p after stages 1..4, + 3p per later
-// stage = < 66p after ten stages, still far inside the 768-bit container (p < 2^753) and inside reduce_small's domain.
-template <int THREADS, int MIN_BLOCKS, bool LZ>
+// CTA-wide enumeration of the butterflies of every stage, one __syncthreads per stage, values in [0, 2p) between stages.
+// Stages 2..4 are enumerated twiddle-major, so the butterflies with a unit twiddle fill whole warps and skip the
+// product (1.875 of 10 stages' worth).  (A wide-lazy-range form of this kernel measured 2 % slower and was removed.)
+template <int THREADS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 ntt768_pass(const uint32_t *src, uint32_t *dst, const uint32_t *__restrict__ wloc, const __grid_constant__ PassGeom g,
             const __grid_constant__ PreDesc pd, const __grid_constant__ PreDesc post, const __grid_constant__ ScatterDesc sc,
@@ -238,52 +236,28 @@ ntt768_pass(const uint32_t *src, uint32_t *dst, const uint32_t *__restrict__ wlo
                 wp = wloc + (size_t)((jj << (lq - ph)) << g.wloc_shift) * TW_WORDS;
             }
             uint4 *sh = tile + slot_of(hi) * SMEM_PITCH4;
-            uint32_t t[NL], d[NL];  // d = K p - t (wide lazy ranges only)
+            uint32_t t[NL];
             if (unit) {
                 lds_elem(t, sh);  // unit twiddle
-                if (LZ) {         // K = 3 * 2^(ph - 1)
-                    uint32_t kp[NL];
-                    const uint32_t sft = ph - 1;
-                    kp[0] = fc.p3[0] << sft;
-#pragma unroll
-                    for (int k = 1; k < NL; ++k) kp[k] = __funnelshift_l(fc.p3[k - 1], fc.p3[k], sft);
-                    neg_wide(d, kp, t);
-                }
             } else {
                 // fixed-operand product: the data streams from shared memory (twice), the twiddle's (w, w'') from the table
                 SmemWords x1{sh, make_uint4(0, 0, 0, 0)}, x2{sh, make_uint4(0, 0, 0, 0)};
-                uint32_t w2[NL];
-                load_tw_half(w2, wp + NL);
-                shoup_mul_3p(fc, t, x1, x2, w2, wp);
-                if (LZ) neg_wide(d, fc.p3, t);
-                else cond_sub(t, fc.p2);
+                shoup_mul_lazy(fc, t, x1, x2, wp);
             }
             if (elementwise) {
-                if (g.canonical && ph == ph_last) {  // t in [0, 3p) (LZ) or [0, 2p)
-                    if (LZ) cond_sub(t, fc.p2);
-                    cond_sub(t, fc.p);
-                }
+                if (g.canonical && ph == ph_last) canonicalize(fc, t);
                 sts_elem(sh, t);
             } else {
                 uint4 *sl = tile + slot_of(lo) * SMEM_PITCH4;
                 uint32_t u[NL], x[NL];
                 lds_elem(u, sl);
                 const bool last = g.canonical && ph == ph_last;
-                if (LZ) {
-                    add_raw(x, u, t);
-                    if (last) reduce_small(fc, x);
-                    sts_elem(sl, x);
-                    add_raw(x, u, d);
-                    if (last) reduce_small(fc, x);
-                    sts_elem(sh, x);
-                } else {
-                    add_lazy(fc, x, u, t);
-                    if (last) canonicalize(fc, x);
-                    sts_elem(sl, x);
-                    sub_lazy(fc, x, u, t);
-                    if (last) canonicalize(fc, x);
-                    sts_elem(sh, x);
-                }
+                add_lazy(fc, x, u, t);
+                if (last) canonicalize(fc, x);
+                sts_elem(sl, x);
+                sub_lazy(fc, x, u, t);
+                if (last) canonicalize(fc, x);
+                sts_elem(sh, x);
             }
         }
         __syncthreads();
@@ -319,8 +293,8 @@ ntt768_pass(const uint32_t *src, uint32_t *dst, const uint32_t *__restrict__ wlo
 //             stores the elements it owns.
 // One CTA barrier per tile instead of one per stage: the eight warps drift apart, so one warp's global loads, twiddle
 // fetches and add/sub carry chains overlap the other warps' products instead of lining up behind a barrier.
-// FLAGS: 1 = wide lazy ranges (no conditional subtractions inside the pass, see fp768.cuh), 2 = prefetch the next work
-// item's w'' before the add/sub of the current one.
+// FLAGS: 1 = wide lazy ranges (no conditional subtractions inside the pass, see fp768.cuh; always set in the shipped
+// instantiations), 2 = prefetch the next work item's w'' before the add/sub of the current one.
 // Unit twiddles: all of stage 1 and the jj == 0 half of stage 2 (enumerated twiddle-major: one whole iteration) skip the
 // product; in later stages the jj == 0 lanes multiply by table entry 0 = (1, floor(2^768/p)).
 constexpr int V2_LAZY = 1, V2_PREFETCH = 2;

@@ -28,6 +28,11 @@ def from_limbs(l):
     return sum(int(v) << (32 * i) for i, v in enumerate(np.asarray(l).reshape(-1)))
 
 
+def to_mont768(x, p=FR):
+    """integer x -> Montgomery-form limbs of x mod p"""
+    return to_limbs(x % p * RMONT % p)
+
+
 def mont_pow(w_limbs, e, p=FR):
     """(w^e) for w given and returned in Montgomery form"""
     w = from_limbs(w_limbs) * pow(RMONT, -1, p) % p

@@ -198,14 +198,38 @@ class Context:
         self._check(self.L.gsn_fp768_inner_product_host(self._h, _ptr(out), _ptr(a), _ptr(b), a.shape[0]))
         return out
 
-    def g1_multiexp(self, points, scalars):
+    def fp2_binop(self, op, a, b):
+        """element-wise Fq2 = Fq[u]/(u^2 - 13) arithmetic on (count, 2, 24) arrays (the reference's fp2)"""
+        a = np.ascontiguousarray(a, dtype=np.uint32).reshape(-1, 2, NL)
+        b = np.ascontiguousarray(b, dtype=np.uint32).reshape(-1, 2, NL)
+        out = np.empty_like(a)
+        self._check(self.L.gsn_fp2_binop_host(self._h, {"mul": 0, "add": 1, "sub": 2}[op], _ptr(out), _ptr(a), _ptr(b), a.shape[0]))
+        return out
+
+    def g1_multiexp(self, points, scalars, method="auto", window_bits=0):
         """sum_i scalars[i] * points[i] on MNT4-753 G1 -- the reference's multiexp<mnt4753_G1, Scalar>.  points: (n, 3, 24)
-        projective Montgomery limbs over Fq; scalars: (n, 24) raw integers.  (Fq is built in: any context field works.)"""
+        projective Montgomery limbs over Fq; scalars: (n, 24) raw integers.  (Fq is built in: any context field works.)
+        method: "auto", "naive" (the reference's algorithm) or "bucket" (Pippenger); window_bits 0 = automatic."""
         points = np.ascontiguousarray(points, dtype=np.uint32).reshape(-1, 3, NL)
         scalars = np.ascontiguousarray(scalars, dtype=np.uint32).reshape(-1, NL)
         assert points.shape[0] == scalars.shape[0]
+        n = points.shape[0]
         out = np.empty((3, NL), dtype=np.uint32)
-        self._check(self.L.gsn_g1_multiexp_host(self._h, _ptr(out), _ptr(points), _ptr(scalars), points.shape[0]))
+        if method == "auto" and window_bits == 0:
+            self._check(self.L.gsn_g1_multiexp_host(self._h, _ptr(out), _ptr(points), _ptr(scalars), n))
+            return out
+        dp, ds, do = self.device_alloc(max(n, 1) * 288), self.device_alloc(max(n, 1) * 96), self.device_alloc(288)
+        try:
+            if n:
+                self.h2d(dp, points)
+                self.h2d(ds, scalars)
+            self._check(self.L.gsn_g1_multiexp_device_ex(self._h, C.c_void_p(do), C.c_void_p(dp), C.c_void_p(ds), n,
+                                                         {"auto": 0, "naive": 1, "bucket": 2}[method], int(window_bits), None))
+            self.synchronize()
+            self.d2h(out, do)
+        finally:
+            for p in (dp, ds, do):
+                self.device_free(p)
         return out
 
     def coset_ntt768(self, a, omega, shift, inverse=False):
@@ -299,6 +323,9 @@ class FourStepPlan:
         x = C.c_void_p()
         self.ctx._check(self.L.gsn_fourstep_inverse(self._h, C.c_void_p(stream or 0), C.byref(x)))
         return x.value
+
+    def set_timing(self, on):
+        self.ctx._check(self.L.gsn_fourstep_set_timing(self._h, int(bool(on))))
 
     def phase_ms(self):
         ms = (C.c_float * 3)()

@@ -10,6 +10,11 @@
 // and validated, and failures are reported by a std::runtime_error carrying gsn_last_error().
 // best_ifft is the inverse (omega^-1, n^-1), which the reference does not have.
 #pragma once
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -23,22 +28,57 @@
 
 namespace gsn {
 
-// one process-wide context per device for the template entry points
-inline gsn_ctx *default_ctx(int device = 0) {
-    static gsn_ctx *ctx[16] = {nullptr};
-    if (device < 0 || device >= 16) throw std::runtime_error("gsn::default_ctx: device out of range");
-    if (!ctx[device] && gsn_ctx_create(&ctx[device], device) != GSN_OK)
-        throw std::runtime_error(std::string("gsn_ctx_create: ") + gsn_last_error());
-    return ctx[device];
-}
 inline void check(int rc, const char *what) {
     if (rc != GSN_OK) throw std::runtime_error(std::string(what) + ": " + gsn_last_error());
+}
+// one process-wide context per device for the template entry points (created once, thread safe)
+inline gsn_ctx *default_ctx(int device = 0) {
+    static gsn_ctx *ctx[16] = {nullptr};
+    static std::mutex mu;
+    if (device < 0 || device >= 16) throw std::runtime_error("gsn::default_ctx: device out of range");
+    std::lock_guard<std::mutex> lk(mu);
+    if (!ctx[device]) check(gsn_ctx_create(&ctx[device], device), "gsn_ctx_create");
+    return ctx[device];
+}
+// Transforms of 2^24 elements and more are sharded over every visible GPU (1, 2, 4 or 8 of them; the four-step plan of
+// gsn_multi_*, peer access between the devices of this one process).  GSN_MULTI_MIN_LOG_N overrides the threshold,
+// GSN_MULTI_DEVICES caps the device count (1 disables sharding).  Plans are cached per (n, omega).
+inline gsn_multi *default_multi(size_t n, const uint32_t *omega) {
+    struct Entry { size_t n; uint32_t omega[GSN_FP768_LIMBS]; gsn_multi *m; };
+    static std::vector<Entry> cache;
+    static std::mutex mu;
+    static int devices = -1;
+    std::lock_guard<std::mutex> lk(mu);
+    if (devices < 0) {
+        int cnt = 0;
+        gsn_device_count(&cnt);
+        if (const char *e = std::getenv("GSN_MULTI_DEVICES")) cnt = std::min(cnt, std::atoi(e));
+        devices = 1;
+        while (devices * 2 <= cnt && devices < 8) devices *= 2;
+    }
+    const char *e = std::getenv("GSN_MULTI_MIN_LOG_N");
+    const unsigned min_log = e ? (unsigned)std::atoi(e) : 24u;
+    if (devices < 2 || n < ((size_t)1 << min_log) || (n & (n - 1))) return nullptr;
+    for (auto &c : cache)
+        if (c.n == n && std::memcmp(c.omega, omega, sizeof(c.omega)) == 0) return c.m;
+    int ids[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+    Entry ent;
+    ent.n = n;
+    std::memcpy(ent.omega, omega, sizeof(ent.omega));
+    check(gsn_multi_create(&ent.m, ids, (unsigned)devices, n, omega, 3), "gsn_multi_create");
+    if (cache.size() >= 2) { gsn_multi_destroy(cache.front().m); cache.erase(cache.begin()); }
+    cache.push_back(ent);
+    return ent.m;
 }
 
 template <typename FieldT> struct fft_dispatch;  // no generic definition: unknown field types do not link silently
 
 template <> struct fft_dispatch<fields::Scalar> {
     static void run(std::vector<fields::Scalar> &a, const fields::Scalar &omg, int inverse) {
+        if (gsn_multi *m = default_multi(a.size(), omg.im_rep)) {
+            check(gsn_multi_ntt768_host(m, reinterpret_cast<uint32_t *>(a.data()), inverse), "gsn_multi_ntt768_host");
+            return;
+        }
         check(gsn_ntt768_host(default_ctx(), reinterpret_cast<uint32_t *>(a.data()), a.size(), omg.im_rep, inverse), "gsn_ntt768_host");
     }
 };

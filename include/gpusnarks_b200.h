@@ -67,7 +67,8 @@ int gsn_set_field768(gsn_ctx *ctx, int field);
  * the boundary's sub-problem, one product per element) larger than this is replaced by two-level tables of
  * 2 * sqrt(n) entries and two products per element -- 2^26 needs 3 MB instead of 13 GB.  GSN_OPT_PLAN_CACHE_BYTES
  * (default 16 GiB, and at most 16 plans): least-recently-used plans are dropped beyond it.  GSN_OPT_KERNEL_VARIANT:
- * -1 = small-tile kernel only, 0..3 = flag bits of the large-tile kernel (1 wide lazy ranges, 2 twiddle prefetch; default 3). */
+ * kernel used for 1024-element tiles: 4 (or -1, default) = CTA-wide stages, 1 = warp-owned tiles with wide lazy ranges,
+ * 3 = the same with twiddle prefetch (see DESIGN.md for the measurements). */
 #define GSN_OPT_FLAT_TABLE_LIMIT 1
 #define GSN_OPT_PLAN_CACHE_BYTES 2
 #define GSN_OPT_KERNEL_VARIANT 3
@@ -149,8 +150,10 @@ int gsn_fourstep_buffers(gsn_fourstep *plan, void **x, void **y0, void **y1, voi
 int gsn_fourstep_connect(gsn_fourstep *plan, void *const *peer_x, void *const *peer_y0, void *const *peer_y1, void *const *peer_flags);
 int gsn_fourstep_forward(gsn_fourstep *plan, void *stream, void **y_out);
 int gsn_fourstep_inverse(gsn_fourstep *plan, void *stream, void **x_out);
-/* mean milliseconds of the three forward phases (column transforms + scatter, signal/barrier, row transforms); only
- * collected when the environment variable GSN_FOURSTEP_TIMING is set (it synchronises inside forward) */
+/* mean milliseconds of the three forward phases (column transforms + scatter, signal/barrier, row transforms) over the
+ * calls since gsn_fourstep_set_timing(plan, 1).  Timing synchronises the host inside forward(): switch it on for a
+ * few calls outside the measured region (one process per GPU only). */
+int gsn_fourstep_set_timing(gsn_fourstep *plan, int on);
 int gsn_fourstep_phase_ms(gsn_fourstep *plan, float ms[3], uint64_t *calls);
 
 /* ---- multi-GPU transform from ONE process: what a C++ caller of best_fft (reference cuda/fft_kernel.h:24-25) reaches
@@ -223,10 +226,21 @@ int gsn_fp768_inner_product_host(gsn_ctx *ctx, uint32_t out[GSN_FP768_LIMBS], co
  * The curve's base field MNT4-753 Fq is built in: these calls do not depend on gsn_set_field768.  Points are
  * homogeneous projective (X, Y, Z), 3 x 24 limbs each, Montgomery form, identity = any point with Z = 0;
  * scalars are raw 768-bit little-endian integers (the reference reads their bits with hasBitAt).  The result
- * is projective with canonical coordinates.  Algorithm as in the reference: one double-and-add per point,
- * then a tree reduction (not a bucket method). */
+ * is projective with canonical coordinates (any representative of the point: compare as affine points).
+ * Algorithm: the bucket method (Pippenger) -- signed c-bit windows, points sorted by (window, bucket), one thread per
+ * bucket, a running-sum reduction per window, Horner over the window sums on the host; blocking.  _ex selects the
+ * method (0 automatic, 1 the reference's own algorithm: one double-and-add per point then a tree reduction, 2 bucket
+ * method) and the window width (0 automatic, else 2..16). */
 int gsn_g1_multiexp_host(gsn_ctx *ctx, uint32_t out[72], const uint32_t *points, const uint32_t *scalars, size_t n);
 int gsn_g1_multiexp_device(gsn_ctx *ctx, uint32_t *d_out, const uint32_t *d_points, const uint32_t *d_scalars, size_t n, void *stream);
+int gsn_g1_multiexp_device_ex(gsn_ctx *ctx, uint32_t *d_out, const uint32_t *d_points, const uint32_t *d_scalars, size_t n, unsigned method,
+                              unsigned window_bits, void *stream);
+
+/* ---- Fq2 = Fq[u]/(u^2 - 13) element-wise arithmetic: the reference's `fp2` (cuda/device_field.h:220-294; the
+ * extension field of MNT4-753's G2).  Elements are (x, y) = x + y u, 2 x 24 limbs, Montgomery form over Fq (built in,
+ * independent of gsn_set_field768).  op: 0 mul (Karatsuba, as the reference), 1 add, 2 sub; canonical outputs. */
+int gsn_fp2_binop_host(gsn_ctx *ctx, int op, uint32_t *out, const uint32_t *a, const uint32_t *b, size_t count);
+int gsn_fp2_binop_device(gsn_ctx *ctx, int op, uint32_t *d_out, const uint32_t *d_a, const uint32_t *d_b, size_t count, void *stream);
 
 /* ---- 32-bit NTT over Z/mod (mod an odd prime < 2^31 with n | mod-1).
  * Replaces best_fft for the reference's 32-bit field sketch (fields/dummy_field.h:24-62). */

@@ -61,3 +61,16 @@ def test_cpp_drop_in_driver_runs():
     out = subprocess.run([exe, "16", "20"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("DONE") == 2 and "MISMATCH" not in out.stdout and "Missmatch" not in out.stdout
+
+
+def test_cpp_best_fft_shards_over_the_visible_gpus():
+    """the same reference-shaped C++ driver, with the sharding threshold lowered to 2^18: best_fft<fields::Scalar> then goes
+    through gsn_multi_* (one process, every visible GPU, peer access) and must still equal the host FFT"""
+    import gpusnarks_b200 as g
+    if g.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2): with one device best_fft keeps to gsn_ntt768_host")
+    exe = os.path.join(ROOT, "tests", "cpp", "test_fft_main")
+    env = dict(os.environ, GSN_MULTI_MIN_LOG_N="18")
+    out = subprocess.run([exe, "18", "16"], capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("DONE") == 2 and "MISMATCH" not in out.stdout and "Missmatch" not in out.stdout

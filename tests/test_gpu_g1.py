@@ -96,3 +96,82 @@ def test_reference_test_shape_linearity(fq_ctx):
     # and against the model, folding equal points first: sum_i s_i P_(i mod 8) = sum_j (sum of s over class j) P_j
     folded = [sum(s[j::8]) for j in range(8)]
     assert a == g1ref.multiexp(base, folded)
+
+
+@pytest.mark.parametrize("n,seed,c", [(8, 21, 2), (9, 22, 3), (33, 23, 5), (100, 24, 0), (300, 25, 7), (513, 26, 0)])
+def test_bucket_method_equals_group_law(fq_ctx, n, seed, c):
+    """Pippenger (signed windows, buckets, running sums, host Horner) against the affine group law, several window
+    widths; equal points, inverse pairs and identities mixed in (they exercise the doubling / identity cases inside the
+    bucket sums) and scalars with the top bits set (carry into the extra window)"""
+    rng = random.Random(seed)
+    pts = [g1ref.random_point(rng) for _ in range(n)]
+    pts[1] = pts[0]                                            # same point twice
+    pts[2] = (pts[0][0], (g1ref.Q - pts[0][1]) % g1ref.Q)      # its inverse
+    if n > 5:
+        pts[5] = None                                          # identity input
+    ks = [rng.randrange(pyref.FR) for _ in range(n)]
+    ks[0] = ks[1] = ks[2] = 3                                  # same bucket: P + P (doubling) then + (-P)
+    ks[3] = (1 << 768) - 1                                     # every signed digit carries
+    ks[4] = 0
+    out = fq_ctx.g1_multiexp(_pack_points(pts), pyref.ints_to_array(ks), method="bucket", window_bits=c)
+    assert _affine(out) == g1ref.multiexp(pts, ks)
+    for cc in range(3):
+        assert pyref.from_limbs(out[cc]) < g1ref.Q
+
+
+def test_bucket_method_equals_naive_method_2pow12(fq_ctx):
+    """both algorithms on 2^12 points with full-width scalars give the same affine point"""
+    rng = random.Random(31)
+    base = [g1ref.random_point(rng) for _ in range(16)]
+    n = 1 << 12
+    P = _pack_points(base)[np.arange(n) % 16]
+    ks = pyref.ints_to_array([rng.randrange(pyref.FR) for _ in range(n)])
+    a = _affine(fq_ctx.g1_multiexp(P, ks, method="naive"))
+    b = _affine(fq_ctx.g1_multiexp(P, ks, method="bucket"))
+    assert a == b
+    folded = [sum(pyref.from_limbs(k) for k in ks[j::16]) for j in range(16)]
+    assert a == g1ref.multiexp(base, folded)
+
+
+def test_fp2_arithmetic(fq_ctx):
+    """the reference's fp2 (Fq2 = Fq[u]/(u^2 - 13), cuda/device_field.h:220-294) against Python integers"""
+    import fieldgen
+    q = g1ref.Q
+    n = 500
+    a = np.stack([fieldgen.random_elements(n, 61, q), fieldgen.random_elements(n, 62, q)], axis=1)
+    b = np.stack([fieldgen.random_elements(n, 63, q), fieldgen.random_elements(n, 64, q)], axis=1)
+    a[0] = 0
+    b[1] = 0
+    a[2, 0] = pyref.to_limbs(q - 1)
+    a[2, 1] = pyref.to_limbs(q - 1)
+    rinv = pow(pyref.RMONT, -1, q)
+
+    def ints(v):
+        return [(pyref.from_limbs(r[0]) * rinv % q, pyref.from_limbs(r[1]) * rinv % q) for r in v]
+    A, B = ints(a), ints(b)
+    for op in ("mul", "add", "sub"):
+        got = ints(fq_ctx.fp2_binop(op, a, b))
+        for (x, y), (X, Y), g_ in zip(A, B, got):
+            if op == "mul":
+                exp = ((x * X + 13 * y * Y) % q, (x * Y + y * X) % q)
+            elif op == "add":
+                exp = ((x + X) % q, (y + Y) % q)
+            else:
+                exp = ((x - X) % q, (y - Y) % q)
+            assert g_ == exp, op
+
+
+def test_cpp_multiexp_driver_runs(tmp_path):
+    """tests/cpp/test_multiexp_main.cpp = the reference's test_multiexp / test_multiexp_mnt4753_G1 drivers (reference
+    test/main.cpp:89-179) through cuda/multi_exp.h: device multiexp == the reference's host loop, for Scalar x Scalar
+    and for 24 curve points x full-width scalars (bucket method on the device, double-and-add on the host)"""
+    import subprocess
+    import test_host_cpp
+    rng = random.Random(41)
+    pts = [g1ref.random_point(rng) for _ in range(24)]
+    path = tmp_path / "points.bin"
+    path.write_bytes(_pack_points(pts).tobytes())
+    exe = test_host_cpp.build_multiexp_driver(tmp_path)
+    out = subprocess.run([exe, str(path), "24", "12"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("DONE") == 2 and "Missmatch" not in out.stdout

@@ -42,6 +42,88 @@ def test_reference_main_cpp_compiles_unmodified(tmp_path):
     assert os.path.exists(exe)
 
 
+def test_reference_main_cpp_compiles_unmodified_multiexp_mode(tmp_path):
+    """the same file WITHOUT -DFFT (test_multiexp and test_multiexp_mnt4753_G1, reference test/main.cpp:89-179): needs
+    cuda/multi_exp.h, multiexp<Scalar,Scalar>, multiexp<mnt4753_G1,Scalar>, fields::mnt4753_G1 and its operators"""
+    import pytest
+    ref = "/root/reference/test/main.cpp"
+    if not os.path.exists(ref):
+        pytest.skip("reference tree absent")
+    from gpusnarks_b200 import build
+    build.build()
+    exe = str(tmp_path / "ref_main_multiexp")
+    subprocess.check_call([CXX, "-O2", "-fopenmp", "-std=c++17", "-w", "-I" + os.path.join(ROOT, "include"), "-I/root/reference/test",
+                           ref, "-L" + os.path.join(ROOT, "gpusnarks_b200"), "-lgpusnarks_b200",
+                           "-Wl,-rpath," + os.path.join(ROOT, "gpusnarks_b200"), "-o", exe])
+    assert os.path.exists(exe)
+
+
+def build_multiexp_driver(out_dir):
+    from gpusnarks_b200 import build
+    build.build()
+    exe = os.path.join(str(out_dir), "test_multiexp_main")
+    subprocess.check_call([CXX, "-O2", "-std=c++17", "-Wall", "-I" + os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(ROOT, "tests", "cpp", "test_multiexp_main.cpp"), "-L" + os.path.join(ROOT, "gpusnarks_b200"),
+                           "-lgpusnarks_b200", "-Wl,-rpath," + os.path.join(ROOT, "gpusnarks_b200")])
+    return exe
+
+
+def test_multiexp_driver_compiles(tmp_path):
+    """the reference-shaped multi-exponentiation driver builds against cuda/multi_exp.h (it runs under -m gpu)"""
+    assert os.path.exists(build_multiexp_driver(tmp_path))
+
+
+def test_host_g1_and_fp2_types_match_the_python_model(tmp_path):
+    """fields::mnt4753_G1 / fields::fp2 host arithmetic (include/cuda/device_field.h, include/fields/g1_host.h) against
+    tests/g1ref.py: a small C++ program computes k*P + Q and an fp2 product, Python checks the numbers"""
+    import random
+    import numpy as np
+    import g1ref
+    import pyref
+    src = tmp_path / "g1host.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include <cuda/device_field.h>
+int main(int argc, char **argv) {
+    FILE *f = fopen(argv[1], "rb");
+    fields::mnt4753_G1 P, Q; fields::Scalar k; fields::fp2 a, b;
+    if (fread(&P, 288, 1, f) != 1 || fread(&Q, 288, 1, f) != 1 || fread(&k, 96, 1, f) != 1 || fread(&a, 192, 1, f) != 1 || fread(&b, 192, 1, f) != 1) return 2;
+    fclose(f);
+    fields::mnt4753_G1 R = P * k + Q, Z = P - P, D = P + P;
+    fields::fp2 c = a * b;
+    f = fopen(argv[2], "wb");
+    fwrite(&R, 288, 1, f); fwrite(&Z, 288, 1, f); fwrite(&D, 288, 1, f); fwrite(&c, 192, 1, f);
+    fclose(f);
+    return 0;
+}
+''')
+    exe = str(tmp_path / "g1host")
+    subprocess.check_call([CXX, "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), "-o", exe, str(src)])
+    rng = random.Random(77)
+    q = g1ref.Q
+    P, Qp = g1ref.random_point(rng), g1ref.random_point(rng)
+    k = rng.randrange(pyref.FR)
+    a = (rng.randrange(q), rng.randrange(q))
+    b = (rng.randrange(q), rng.randrange(q))
+
+    def pt(Pt):
+        return b"".join(np.array(pyref.to_limbs(v), dtype=np.uint32).tobytes() for v in g1ref.to_projective_mont(Pt))
+
+    def fq(v):
+        return np.array(pyref.to_limbs(v * pyref.RMONT % q), dtype=np.uint32).tobytes()
+    (tmp_path / "in.bin").write_bytes(pt(P) + pt(Qp) + np.array(pyref.to_limbs(k), dtype=np.uint32).tobytes() + fq(a[0]) + fq(a[1]) + fq(b[0]) + fq(b[1]))
+    subprocess.check_call([exe, str(tmp_path / "in.bin"), str(tmp_path / "out.bin")])
+    out = np.frombuffer((tmp_path / "out.bin").read_bytes(), dtype=np.uint32)
+    R, Z, D = (out[i * 72:(i + 1) * 72].reshape(3, 24) for i in range(3))
+    c = out[216:264].reshape(2, 24)
+    aff = lambda m: g1ref.from_projective_mont(*[pyref.from_limbs(m[j]) for j in range(3)])
+    assert aff(R) == g1ref.add(g1ref.mul(k, P), Qp)
+    assert aff(Z) is None and aff(D) == g1ref.mul(2, P)
+    rinv = pow(pyref.RMONT, -1, q)
+    got = (pyref.from_limbs(c[0]) * rinv % q, pyref.from_limbs(c[1]) * rinv % q)
+    assert got == ((a[0] * b[0] + 13 * a[1] * b[1]) % q, (a[0] * b[1] + a[1] * b[0]) % q)
+
+
 def _build_c_smoke(tmp_path):
     from gpusnarks_b200 import build
     build.build()

@@ -24,7 +24,7 @@ def main():
         a = rng.integers(0, 1 << 32, size=(n, 24), dtype=np.uint64).astype(np.uint32)
         a[:, 23] &= 0xFFFF
         ref = None
-        for variant, limit in [(4, None), (5, None), (1, None), (3, None), (1, 1 << 16), (5, 1 << 16)]:
+        for variant, limit in [(4, None), (1, None), (3, None), (4, 1 << 16), (1, 1 << 16)]:
             ctx = g.Context(0)
             ctx.set_option("kernel_variant", variant)
             if limit:
