@@ -152,9 +152,10 @@ def spot_check(a_host, omega, got_rows, ks, inverse_of=None):
     return bool((exp == got_rows).all())
 
 
-def ncu_traffic_bytes(name):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    summary of one `ncu --set full` capture (profiles/<name>.raw.csv, made by tools/summarize_ncu.py)"""
+def ncu_traffic_bytes(name, per="launch", divide=1.0):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed summary of one
+    `ncu --set full` capture (profiles/<name>.raw.csv, made by tools/summarize_ncu.py): the mean per launch, or
+    (per="sum") the sum over the captured launches divided by `divide`"""
     import csv
     path = os.path.join(ROOT, "profiles", name + ".raw.csv")
     try:
@@ -163,7 +164,7 @@ def ncu_traffic_bytes(name):
         ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         tot = [float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]] for r in rows[2:]]
-        return sum(tot) / len(tot)
+        return sum(tot) / divide if per == "sum" else sum(tot) / len(tot)
     except Exception:
         return None
 
@@ -203,7 +204,9 @@ def bench_ntt32(ctx, hbm_peak_gbs, logn=22, batch=16, reps=12):
             "us_per_transform": t * 1e6, "value": butterflies(logn) / t, "unit": "butterflies/s",
             "roofline": {"kernel": "gsn::ntt32_fast_pass<4,4,3,...>", "bound": "hbm", "achieved": alg / t / 1e9, "peak": hbm_peak_gbs, "unit": "GB/s",
                          "frac": alg / t / 1e9 / hbm_peak_gbs, "algorithmic_bytes_per_transform": alg,
-                         "traffic": ncu_traffic_bytes("ntt32_fast_pass_r01")}}
+                         # the capture is the two passes of ONE 16-buffer batch (tools/run_ntt32_once.py 22 4 16): per transform = sum / 16
+                         "traffic": ncu_traffic_bytes("ntt32_fast_pass_r02_batch16", per="sum", divide=16.0),
+                         "traffic_note": "dram bytes of both passes of a 16-transform batch / 16 (profiles/ntt32_fast_pass_r02_batch16.md): the HBM-resident configuration timed here"}}
 
 
 # ------------------------------------------------------------------------------ main
@@ -271,7 +274,7 @@ def roofline_block(value, N, logn, ms_step, rates, single, kernels_per_step, ker
         "int32_issue_rates_per_s": rates["rates"],
         "launches_per_step": kernels_per_step,
         "avg_launch_ms": (ms_step / kernels_per_step) if kernels_per_step else None,
-        "traffic": ncu_traffic_bytes("ntt768_pass_r02") or ncu_traffic_bytes("ntt768_pass_r01"),
+        "traffic": ncu_traffic_bytes("ntt768_pass_r02_cta_wide") or ncu_traffic_bytes("ntt768_pass_r01"),
         "table_bytes": table_bytes,
         "hbm": {"algorithmic_bytes_per_step": alg_bytes, "achieved_gbs": (alg_bytes / (ms_step * 1e-3) / 1e9) if alg_bytes else None,
                 "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650",

@@ -266,28 +266,74 @@ __device__ __forceinline__ uint64_t g1_lower_bound(const uint32_t *keys, uint64_
     return lo;
 }
 
-// one thread per (window, bucket): buckets[key] = sum of the (signed) points whose sorted key equals `key`
+__device__ __forceinline__ void g1_load_signed(G1 &P, const uint32_t *points, uint32_t v) {
+    g1_load(P, points + (uint64_t)(v >> 1) * 3 * NL);
+    if (v & 1) {  // -P = (X, -Y, Z)
+        uint32_t zero[NL];
+        for (int i = 0; i < NL; ++i) zero[i] = 0;
+        fq_sub(P.y, zero, P.y);
+    }
+}
+
+// one thread per (window, bucket): buckets[key] = sum of the (signed) points whose sorted key equals `key`.
+// A bucket with more than `limit` points would serialise one thread (scalars far below 2^768 leave the top windows with
+// a handful of digit values, each shared by a large fraction of the points): it is queued for g1_heavy_bucket_kernel.
 __global__ void __launch_bounds__(128) g1_bucket_kernel(uint32_t *buckets, const uint32_t *points, const uint32_t *keys, const uint32_t *vals,
-                                                        uint64_t pairs, uint32_t nbuckets, uint32_t bs) {
+                                                        uint64_t pairs, uint32_t nbuckets, uint32_t bs, uint32_t limit, uint32_t *heavy,
+                                                        uint32_t *heavy_count) {
     const uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
     if (key >= nbuckets) return;
     G1 acc, P, t;
     g1_set_identity(acc);
     if (key % bs != 0) {
-        uint64_t lo = g1_lower_bound(keys, pairs, key);
-        for (; lo < pairs && keys[lo] == key; ++lo) {
-            const uint32_t v = vals[lo];
-            g1_load(P, points + (uint64_t)(v >> 1) * 3 * NL);
-            if (v & 1) {  // -P = (X, -Y, Z); lazy values: 2p - Y stays in [0, 2p]... use the field subtraction from zero
-                uint32_t zero[NL];
-                for (int i = 0; i < NL; ++i) zero[i] = 0;
-                fq_sub(P.y, zero, P.y);
+        const uint64_t lo = g1_lower_bound(keys, pairs, key), hi = g1_lower_bound(keys, pairs, key + 1);
+        if (hi - lo > limit) {
+            heavy[atomicAdd(heavy_count, 1u)] = key;
+        } else {
+            for (uint64_t i = lo; i < hi; ++i) {
+                g1_load_signed(P, points, vals[i]);
+                g1_add(t, acc, P);
+                g1_copy(acc, t);
             }
-            g1_add(t, acc, P);
-            g1_copy(acc, t);
         }
     }
     g1_store(buckets + (uint64_t)key * 3 * NL, acc);
+}
+
+// one block per queued bucket: the threads stride over its points, then a shared-memory tree adds the partial sums
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) g1_heavy_bucket_kernel(uint32_t *buckets, const uint32_t *points, const uint32_t *keys, const uint32_t *vals,
+                                                                  uint64_t pairs, const uint32_t *heavy, const uint32_t *heavy_count) {
+    extern __shared__ uint32_t g1_red[];  // THREADS * 72 words
+    for (uint32_t h = blockIdx.x; h < *heavy_count; h += gridDim.x) {
+        const uint32_t key = heavy[h];
+        const uint64_t lo = g1_lower_bound(keys, pairs, key), hi = g1_lower_bound(keys, pairs, key + 1);
+        G1 acc, P, t;
+        g1_set_identity(acc);
+        for (uint64_t i = lo + threadIdx.x; i < hi; i += THREADS) {
+            g1_load_signed(P, points, vals[i]);
+            g1_add(t, acc, P);
+            g1_copy(acc, t);
+        }
+        uint32_t *mine = g1_red + threadIdx.x * 3 * NL;
+        for (int i = 0; i < NL; ++i) { mine[i] = acc.x[i]; mine[NL + i] = acc.y[i]; mine[2 * NL + i] = acc.z[i]; }
+        __syncthreads();
+        for (int half = THREADS / 2; half >= 1; half >>= 1) {
+            if ((int)threadIdx.x < half) {
+                const uint32_t *o = g1_red + (threadIdx.x + half) * 3 * NL;
+                for (int i = 0; i < NL; ++i) { acc.x[i] = mine[i]; acc.y[i] = mine[NL + i]; acc.z[i] = mine[2 * NL + i]; }
+                for (int i = 0; i < NL; ++i) { P.x[i] = o[i]; P.y[i] = o[NL + i]; P.z[i] = o[2 * NL + i]; }
+                g1_add(t, acc, P);
+                for (int i = 0; i < NL; ++i) { mine[i] = t.x[i]; mine[NL + i] = t.y[i]; mine[2 * NL + i] = t.z[i]; }
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < NL; ++i) { acc.x[i] = mine[i]; acc.y[i] = mine[NL + i]; acc.z[i] = mine[2 * NL + i]; }
+            g1_store(buckets + (uint64_t)key * 3 * NL, acc);
+        }
+        __syncthreads();
+    }
 }
 
 // small multiple k * P by double-and-add (k < 2^16)

@@ -1029,32 +1029,43 @@ static int g1_multiexp_pippenger(gsn_ctx *ctx, uint32_t *d_out, const uint32_t *
     const uint32_t windows = (768 + 1 + c - 1) / c, nb = 1u << (c - 1), bs = nb + 1;
     const uint64_t pairs = (uint64_t)n * windows, nbuckets = (uint64_t)windows * bs;
     if (pairs >= (1ull << 31)) return fail(GSN_ERR_TOO_LARGE, "multiexp of %zu points: %llu (point, window) pairs", n, (unsigned long long)pairs);
-    DevBuf keys, vals, keys2, vals2, tmp, buckets, wsum;
-    if ((rc = dev_alloc(keys, pairs * 4)) || (rc = dev_alloc(vals, pairs * 4)) || (rc = dev_alloc(keys2, pairs * 4)) || (rc = dev_alloc(vals2, pairs * 4)) ||
-        (rc = dev_alloc(buckets, nbuckets * 288)) || (rc = dev_alloc(wsum, (size_t)windows * 288))) return rc;
-    gsn::g1_digits_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((uint32_t *)keys.p, (uint32_t *)vals.p, d_scalars, n, c, windows, bs);
+    // one arena from the stream's scratch buffer (no cudaMalloc / cudaFree per call)
     int key_bits = 1;
     while ((1ull << key_bits) < nbuckets) ++key_bits;
     size_t tmp_bytes = 0;
-    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t *)keys.p, (uint32_t *)keys2.p, (const uint32_t *)vals.p, (uint32_t *)vals2.p,
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr, (uint32_t *)nullptr,
                                        (int)pairs, 0, key_bits, st));
-    if ((rc = dev_alloc(tmp, std::max<size_t>(tmp_bytes, 16)))) return rc;
-    CU(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, (const uint32_t *)keys.p, (uint32_t *)keys2.p, (const uint32_t *)vals.p, (uint32_t *)vals2.p,
-                                       (int)pairs, 0, key_bits, st));
-    gsn::g1_bucket_kernel<<<(unsigned)((nbuckets + 127) / 128), 128, 0, st>>>((uint32_t *)buckets.p, d_points, (const uint32_t *)keys2.p,
-                                                                              (const uint32_t *)vals2.p, pairs, (uint32_t)nbuckets, bs);
-    constexpr int WT = 64;
+    const uint32_t limit = 128;
+    const size_t heavy_cap = pairs / limit + 2;
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_keys = 0, o_vals = o_keys + up(pairs * 4), o_keys2 = o_vals + up(pairs * 4), o_vals2 = o_keys2 + up(pairs * 4),
+                 o_tmp = o_vals2 + up(pairs * 4), o_heavy = o_tmp + up(std::max<size_t>(tmp_bytes, 16)), o_buckets = o_heavy + up((heavy_cap + 1) * 4),
+                 o_wsum = o_buckets + up(nbuckets * 288), total_bytes = o_wsum + up((size_t)windows * 288);
+    uint32_t *arena_w;
+    if ((rc = ensure_work(ctx, st, total_bytes, &arena_w))) return rc;
+    char *arena = (char *)arena_w;
+    uint32_t *keys = (uint32_t *)(arena + o_keys), *vals = (uint32_t *)(arena + o_vals), *keys2 = (uint32_t *)(arena + o_keys2), *vals2 = (uint32_t *)(arena + o_vals2);
+    uint32_t *heavy_count = (uint32_t *)(arena + o_heavy), *heavy = heavy_count + 1, *buckets = (uint32_t *)(arena + o_buckets), *wsum = (uint32_t *)(arena + o_wsum);
+    CU(cudaMemsetAsync(heavy_count, 0, 4, st));
+    gsn::g1_digits_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(keys, vals, d_scalars, n, c, windows, bs);
+    CU(cub::DeviceRadixSort::SortPairs(arena + o_tmp, tmp_bytes, (const uint32_t *)keys, keys2, (const uint32_t *)vals, vals2, (int)pairs, 0, key_bits, st));
+    gsn::g1_bucket_kernel<<<(unsigned)((nbuckets + 127) / 128), 128, 0, st>>>(buckets, d_points, keys2, vals2, pairs, (uint32_t)nbuckets, bs, limit, heavy,
+                                                                              heavy_count);
+    constexpr int HT = 128, WT = 256;
+    auto hv = gsn::g1_heavy_bucket_kernel<HT>;
     auto red = gsn::g1_window_reduce_kernel<WT>;
     if (!ctx->smem_configured.count((const void *)red)) {
         CU(cudaFuncSetAttribute(red, cudaFuncAttributeMaxDynamicSharedMemorySize, WT * 288));
+        CU(cudaFuncSetAttribute(hv, cudaFuncAttributeMaxDynamicSharedMemorySize, HT * 288));
         ctx->smem_configured.insert((const void *)red);
     }
-    red<<<windows, WT, WT * 288, st>>>((uint32_t *)wsum.p, (const uint32_t *)buckets.p, c, bs);
-    ctx->launches += 3;
+    hv<<<(unsigned)std::min<size_t>(heavy_cap, (size_t)ctx->sm_count * 4), HT, HT * 288, st>>>(buckets, d_points, keys2, vals2, pairs, heavy, heavy_count);
+    red<<<windows, WT, WT * 288, st>>>(wsum, buckets, c, bs);
+    ctx->launches += 4;
     CU(cudaGetLastError());
     std::vector<gsn::host::G1Host> S(windows);
     static_assert(sizeof(gsn::host::G1Host) == 288, "three 96-byte coordinates");
-    CU(cudaMemcpyAsync(S.data(), wsum.p, (size_t)windows * 288, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(S.data(), wsum, (size_t)windows * 288, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     // Horner over the windows, most significant first: acc = 2^c acc + S_w
     gsn::host::G1Ops ops(gsn::host::fq_field());

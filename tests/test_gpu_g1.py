@@ -175,3 +175,17 @@ def test_cpp_multiexp_driver_runs(tmp_path):
     out = subprocess.run([exe, str(path), "24", "12"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("DONE") == 2 and "Missmatch" not in out.stdout
+
+
+def test_heavy_buckets(fq_ctx):
+    """300 points with the SAME small scalar all land in one bucket (more than the per-thread limit): the heavy-bucket
+    kernel sums them with a block; and scalars below 2^20 leave every higher window empty"""
+    rng = random.Random(51)
+    base = [g1ref.random_point(rng) for _ in range(5)]
+    n = 300
+    pts = [base[i % 5] for i in range(n)]
+    out = fq_ctx.g1_multiexp(_pack_points(pts), pyref.ints_to_array([5] * n), method="bucket", window_bits=4)
+    assert _affine(out) == g1ref.multiexp(base, [5 * 60] * 5)
+    ks = [rng.randrange(1 << 20) for _ in range(n)]
+    out = fq_ctx.g1_multiexp(_pack_points(pts), pyref.ints_to_array(ks), method="bucket")
+    assert _affine(out) == g1ref.multiexp(base, [sum(ks[j::5]) for j in range(5)])
