@@ -401,6 +401,19 @@ def run_single(args, torch, g, F, ctx, dev, stream, logn, config, rates):
         secondary["pipeline"] = bench_pipeline(ctx, torch, dev, stream, logn)
     except Exception as e:
         secondary["pipeline"] = {"error": str(e)}
+    try:   # the N > 1 workload (configs[3], 2^24) on this one GPU: the same-size baseline of the strong-scaling runs
+        n24 = 1 << 24
+        w24 = F.root_of_unity768(n24)
+        d24 = torch.randint(-(1 << 31), (1 << 31) - 1, (n24, 24), dtype=torch.int32, device=dev, generator=gen)
+        d24[:, 23] &= 0xFFFF
+        ms24 = ctx.time_ntt768(d24.data_ptr(), n24, w24, reps=7)
+        m = float(np.median(ms24[2:]))
+        secondary["cfg4_2pow24_on_one_gpu"] = {"workload": "MNT4-753 Fr forward NTT n=2^24, device resident, 1xB200 (three passes of 8 stages)", "ms_per_step": m,
+                                               "value": butterflies(24) / (m * 1e-3), "unit": "butterflies/s", "plan": ctx.plan_info768(n24, w24)}
+        del d24
+        ctx.trim()
+    except Exception as e:
+        secondary["cfg4_2pow24_on_one_gpu"] = {"error": str(e)}
     try:
         secondary["ntt32_cfg2"] = bench_ntt32(ctx, peaks_file().get("hbm_gbs", 6650.0))
     except Exception as e:

@@ -304,12 +304,12 @@ __device__ __forceinline__ void shoup_mul_lazy(GSN_FC, uint32_t *t, XWords x1, X
 
 // ------------------------------------------------------------------ wide lazy ranges
 // Inside a pass nothing but the products reduces: a butterfly with t in [0, K p) maps u -> (u + t, u + K p - t).
-// K = 3 wherever t comes out of a product; the unit-twiddle butterflies take t as it is: stage 1 sees values below 3p
-// (canonical input, or the pre-twiddle product), the unit half of stage 2 values below 6p (K = 6).  Bounds: < 6p after
-// stage 1, < 12p after stage 2, + 3p per further stage = < 36p after a 10-stage pass (p < 2^753, container 2^768).  The
-// product accepts any x < 2^768, and values are brought back to [0, p) once, by reduce_small, where they leave the
-// transform.  That removes three carry-chain passes and two selects from every butterfly.
-// d = K p - t  (kp = fc.p3 or fc.p6)
+// K = 3 wherever t comes out of a product; a unit-twiddle butterfly of stage s (s <= 4) takes t as it is, below
+// 3p 2^(s-1), and uses K = 3 2^(s-1).  Bounds: < 6p after stage 1, < 12p after stage 2, then + 3p per stage (< 36p after ten
+// stages) or, with unit butterflies in stages 3 and 4 as well, < 24p, < 48p and + 3p per later stage (< 66p); p < 2^753,
+// container 2^768.  The product accepts any x < 2^768, and values are brought back to [0, p) once, by reduce_small,
+// where they leave the transform.  That removes three carry-chain passes and two selects from every butterfly.
+// d = K p - t
 __device__ __forceinline__ void neg_wide(uint32_t *d, const uint32_t *kp, const uint32_t *t) {
     d[0] = sub_cc(kp[0], t[0]);
 #pragma unroll

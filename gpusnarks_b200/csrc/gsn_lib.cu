@@ -141,7 +141,7 @@ struct gsn_ctx {
     size_t flat_table_limit = (size_t)4 << 30;   // a pre-twiddle table larger than this becomes two-level
     size_t plan_cache_bytes = (size_t)16 << 30;  // least-recently-used 768-bit plans are dropped beyond this (and beyond 16 plans)
     uint64_t use_clock = 0;
-    int v2_flags = 4;  // kernel for 1024-element tiles: 4 / -1 = CTA-wide, 1 = warp-owned tiles (lazy ranges), 3 = + prefetch
+    int v2_flags = 4;  // kernel for 1024-element tiles: 4 / -1 = CTA-wide, 1 = warp-owned tiles (lazy ranges), 5 = + CTA-wide stages 3-4
     uint64_t launches = 0;
     int sm_count = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -453,10 +453,11 @@ int launch_ntt768_range(gsn_ctx *ctx, Plan768 *pl, uint32_t *d_data, size_t batc
     gsn::ScatterDesc no_scatter;
     memset(&no_scatter, 0, sizeof(no_scatter));
 
-    // kernel variant for 1024-element tiles: 1 / 3 = warp-owned tiles with wide lazy ranges (3: + twiddle prefetch),
-    // 4 (or -1) = CTA-wide kernel.  Smaller tiles always use the CTA-wide kernel.  (Measured on B200 at 2^20: CTA-wide
-    // 1.281 ms, warp-owned lazy 1.297 ms, + prefetch 1.337 ms; strict-range warp-owned 1.408 ms and a lazy CTA-wide
-    // kernel 1.308 ms were built, measured and removed -- profiles/variants_r02.jsonl.)
+    // kernel variant for 1024-element tiles: 1 = warp-owned tiles with wide lazy ranges, 5 = the same with stages 3-4
+    // enumerated CTA-wide (unit-twiddle skips), 4 (or -1) = CTA-wide kernel.  Smaller tiles always use the CTA-wide kernel.
+    // (Measured on B200 at 2^20: CTA-wide 1.280 ms, warp-owned lazy 1.297-1.313 ms, with CTA-wide stages 3-4 1.281 ms; a
+    // register-prefetch form 1.337 ms, a strict-range warp-owned form 1.408 ms and a lazy CTA-wide kernel 1.308 ms were
+    // built, measured and removed -- profiles/variants_r02.jsonl.)
     const int variant = ctx->v2_flags < 0 ? 4 : ctx->v2_flags;
     auto kern = gsn::ntt768_pass<NTT768_THREADS, 2>;
     if (!ctx->smem_configured.count((const void *)kern)) {
@@ -535,8 +536,8 @@ int launch_ntt768_range(gsn_ctx *ctx, Plan768 *pl, uint32_t *d_data, size_t batc
         const gsn::ScatterDesc &sc = (scatter && q + 1 == P) ? *scatter : no_scatter;
         const uint32_t *wloc = (const uint32_t *)pl->wloc.p;
         if (log_tile == 10 && g.log_l >= 1 && (variant < 4 || g.wait_flags)) {   // a pass that waits on arrival flags needs the warp-owned kernel
-            if (variant == 3) rc = launch_pass2<3>(ctx, grid, smem, st, src, dst, wloc, g, pd, post, sc);
-            else rc = launch_pass2<1>(ctx, grid, smem, st, src, dst, wloc, g, pd, post, sc);
+            if (variant == 1) rc = launch_pass2<1>(ctx, grid, smem, st, src, dst, wloc, g, pd, post, sc);
+            else rc = launch_pass2<5>(ctx, grid, smem, st, src, dst, wloc, g, pd, post, sc);   // variant 5, and every pass that waits on arrival flags
             if (rc) return rc;
         } else {
             if (g.wait_flags) return fail(GSN_ERR_INVALID_ARG, "arrival flags need the large-tile kernel");
@@ -604,7 +605,7 @@ int gsn_ctx_create(gsn_ctx **out, int device) {
     for (int d = 0; d < 2; ++d) CU(cudaEventCreateWithFlags(&ctx->ev_io_free[d], cudaEventDisableTiming));
     int rc = set_field(ctx.get(), GSN_FIELD_MNT4753_FR);
     if (rc) return rc;
-    if (const char *v = getenv("GSN_NTT768_VARIANT")) { const int k = atoi(v); if (k == -1 || k == 1 || k == 3 || k == 4) ctx->v2_flags = k; }
+    if (const char *v = getenv("GSN_NTT768_VARIANT")) { const int k = atoi(v); if (k == -1 || k == 1 || k == 5 || k == 4) ctx->v2_flags = k; }
     if (const char *v = getenv("GSN_FLAT_TABLE_LIMIT")) ctx->flat_table_limit = strtoull(v, nullptr, 10);
     *out = ctx.release();
     return GSN_OK;
@@ -670,7 +671,7 @@ int gsn_ctx_set_option(gsn_ctx *ctx, int option, uint64_t value) {
             evict_plans768(ctx, nullptr);
             break;
         case GSN_OPT_KERNEL_VARIANT:
-            if ((int64_t)value != -1 && value != 1 && value != 3 && value != 4) return fail(GSN_ERR_INVALID_ARG, "kernel variant %lld (1, 3, 4 or -1)", (long long)value);
+            if ((int64_t)value != -1 && value != 1 && value != 5 && value != 4) return fail(GSN_ERR_INVALID_ARG, "kernel variant %lld (1, 4, 5 or -1)", (long long)value);
             ctx->v2_flags = (int)(int64_t)value;
             break;
         default: return fail(GSN_ERR_INVALID_ARG, "unknown option %d", option);

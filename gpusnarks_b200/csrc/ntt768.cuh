@@ -293,17 +293,23 @@ ntt768_pass(const uint32_t *src, uint32_t *dst, const uint32_t *__restrict__ wlo
 //             stores the elements it owns.
 // One CTA barrier per tile instead of one per stage: the eight warps drift apart, so one warp's global loads, twiddle
 // fetches and add/sub carry chains overlap the other warps' products instead of lining up behind a barrier.
-// FLAGS: 1 = wide lazy ranges (no conditional subtractions inside the pass, see fp768.cuh; always set in the shipped
-// instantiations), 2 = prefetch the next work item's w'' before the add/sub of the current one.
+// Wide lazy ranges throughout (no conditional subtractions inside the pass, see fp768.cuh).
 // Unit twiddles: all of stage 1 and the jj == 0 half of stage 2 (enumerated twiddle-major: one whole iteration) skip the
 // product; in later stages the jj == 0 lanes multiply by table entry 0 = (1, floor(2^768/p)).
-constexpr int V2_LAZY = 1, V2_PREFETCH = 2;
+// FLAGS & V2_EARLY_CTA: stages 3 and 4 are enumerated CTA-wide and twiddle-major instead (three more CTA barriers), so
+// that their unit-twiddle butterflies fill whole warps and skip the product as in ntt768_pass: 8.125 instead of 8.5
+// stages' worth of products per ten-stage pass.
+constexpr int V2_LAZY = 1, V2_EARLY_CTA = 4;
 
 struct WorkItem {
     const uint32_t *wp;
     uint32_t lo, hi;
     bool unit;
 };
+
+// stage ph of the tile is enumerated CTA-wide (not by the owning warp)
+template <int FLAGS>
+__device__ __forceinline__ bool v2_cta_stage(int ph, uint32_t lq) { return (FLAGS & V2_EARLY_CTA) && (ph == 3 || ph == 4) && ph <= (int)lq; }
 
 template <int FLAGS>
 __device__ __forceinline__ WorkItem v2_locate(const PassGeom &g, const PreDesc &pd, const PreDesc &post, const uint32_t *wloc, uint64_t sub0,
@@ -325,9 +331,14 @@ __device__ __forceinline__ WorkItem v2_locate(const PassGeom &g, const PreDesc &
         w.wp = pre_entry(pd, elem_index(g, sub0 + (pos >> lq), j), ph < 0);
     } else {
         uint32_t jj;
-        v2_butterfly(W, ph, lane + 32 * it, w.lo, jj);
+        if (v2_cta_stage<FLAGS>(ph, lq)) {
+            cta_butterfly(ph, threadIdx.x + 256 * it, w.lo, jj);
+            w.unit = jj == 0;   // warp uniform: jj = (threadIdx.x + 256 it) >> (10 - ph)
+        } else {
+            v2_butterfly(W, ph, lane + 32 * it, w.lo, jj);
+            w.unit = v2_unit(ph, it);
+        }
         w.hi = w.lo + (1u << (ph - 1));
-        w.unit = v2_unit(ph, it);
         w.wp = wloc + (size_t)((jj << (lq - ph)) << g.wloc_shift) * TW_WORDS;
     }
     return w;
@@ -338,7 +349,6 @@ __global__ void __launch_bounds__(256, 2)
 ntt768_pass2(const uint32_t *src, uint32_t *dst, const uint32_t *__restrict__ wloc, const __grid_constant__ PassGeom g,
              const __grid_constant__ PreDesc pd, const __grid_constant__ PreDesc post, const __grid_constant__ ScatterDesc sc,
              const __grid_constant__ FieldConstants768 fc) {
-    constexpr bool LZ = (FLAGS & V2_LAZY) != 0, PF = (FLAGS & V2_PREFETCH) != 0;
     extern __shared__ uint4 tile[];
     const uint32_t lq = g.log_l;  // 1..10, log_tile == 10
     const uint32_t Lm1 = (1u << lq) - 1;
@@ -365,79 +375,57 @@ ntt768_pass2(const uint32_t *src, uint32_t *dst, const uint32_t *__restrict__ wl
     __syncwarp();
 
     const int ph_last = (int)lq + (post.mode == 0 ? 0 : (post.mode == 2 ? 2 : 1));
-    int ph = pd.mode == 0 ? 1 : (pd.mode == 2 ? -1 : 0), it = 0;
-    WorkItem cur = v2_locate<FLAGS>(g, pd, post, wloc, sub0, W, lane, ph, it);
-    uint32_t w2n[NL];
-    if (PF && !cur.unit) load_tw_half(w2n, cur.wp + NL);
-    for (;;) {
-        uint4 *sh = tile + slot_of(cur.hi) * SMEM_PITCH4;
-        uint32_t t[NL], d[NL];  // d = K p - t (wide lazy ranges only)
-        if (cur.unit) {
-            lds_elem(t, sh);
-            if (LZ) {
-                uint32_t kp[NL];
-#pragma unroll
-                for (int k = 0; k < NL; ++k) kp[k] = ph == 1 ? fc.p3[k] : fc.p6[k];
-                neg_wide(d, kp, t);
-            }
-        } else {
-            SmemWords x1{sh, make_uint4(0, 0, 0, 0)}, x2{sh, make_uint4(0, 0, 0, 0)};
-            uint32_t w2[NL];
-            if (PF) {
-#pragma unroll
-                for (int k = 0; k < NL; ++k) w2[k] = w2n[k];
-            } else {
-                load_tw_half(w2, cur.wp + NL);
-            }
-            shoup_mul_3p(fc, t, x1, x2, w2, cur.wp);
-            if (LZ) neg_wide(d, fc.p3, t);
-            else cond_sub(t, fc.p2);
-        }
-        // successor item (warp uniform) and its twiddle prefetch
+    // ONE inlined copy of the product (about 1300 instructions): neither loop may be unrolled
+#pragma unroll 1
+    for (int ph = pd.mode == 0 ? 1 : (pd.mode == 2 ? -1 : 0); ph <= ph_last; ++ph) {
         const bool elementwise = ph <= 0 || ph > (int)lq;
-        int nph = ph, nit = it + 1;
-        if (nit == (elementwise ? 4 : 2)) { ++nph; nit = 0; }
-        const bool more = nph <= ph_last;
-        WorkItem nxt = cur;
-        if (more) {
-            nxt = v2_locate<FLAGS>(g, pd, post, wloc, sub0, W, lane, nph, nit);
-            if (PF && !nxt.unit) load_tw_half(w2n, nxt.wp + NL);
-        }
-        if (elementwise) {
-            if (g.canonical && ph == ph_last) {  // last post-twiddle round: t in [0, 3p) -> [0, p)
-                if (LZ) cond_sub(t, fc.p2);
-                cond_sub(t, fc.p);
+        const bool last = g.canonical && ph == ph_last;
+        const int its = elementwise ? 4 : 2;
+#pragma unroll 1
+        for (int it = 0; it < its; ++it) {
+            const WorkItem cur = v2_locate<FLAGS>(g, pd, post, wloc, sub0, W, lane, ph, it);
+            uint4 *sh = tile + slot_of(cur.hi) * SMEM_PITCH4;
+            uint32_t t[NL], d[NL];  // d = K p - t
+            if (cur.unit) {         // unit twiddle: t is taken as it is, < 3p 2^(ph-1) (ph <= 4), and subtracted from that bound
+                lds_elem(t, sh);
+                uint32_t kp[NL];
+                const uint32_t sft = ph - 1;
+                kp[0] = fc.p3[0] << sft;
+#pragma unroll
+                for (int k = 1; k < NL; ++k) kp[k] = __funnelshift_l(fc.p3[k - 1], fc.p3[k], sft);
+                neg_wide(d, kp, t);
+            } else {
+                SmemWords x1{sh, make_uint4(0, 0, 0, 0)}, x2{sh, make_uint4(0, 0, 0, 0)};
+                uint32_t w2[NL];
+                load_tw_half(w2, cur.wp + NL);
+                shoup_mul_3p(fc, t, x1, x2, w2, cur.wp);
+                if (!elementwise) neg_wide(d, fc.p3, t);
             }
-            sts_elem(sh, t);
-        } else {
-            uint4 *sl = tile + slot_of(cur.lo) * SMEM_PITCH4;
-            uint32_t u[NL], x[NL];
-            lds_elem(u, sl);
-            const bool last = g.canonical && ph == ph_last;
-            if (LZ) {
+            if (elementwise) {
+                if (last) {  // last post-twiddle round: t in [0, 3p) -> [0, p)
+                    cond_sub(t, fc.p2);
+                    cond_sub(t, fc.p);
+                }
+                sts_elem(sh, t);
+            } else {
+                uint4 *sl = tile + slot_of(cur.lo) * SMEM_PITCH4;
+                uint32_t u[NL], x[NL];
+                lds_elem(u, sl);
                 add_raw(x, u, t);
                 if (last) reduce_small(fc, x);
                 sts_elem(sl, x);
                 add_raw(x, u, d);
                 if (last) reduce_small(fc, x);
                 sts_elem(sh, x);
-            } else {
-                add_lazy(fc, x, u, t);
-                if (last) canonicalize(fc, x);
-                sts_elem(sl, x);
-                sub_lazy(fc, x, u, t);
-                if (last) canonicalize(fc, x);
-                sts_elem(sh, x);
             }
         }
-        if (!more) break;
-        if (nph != ph) {
-            if (nph == 8 && lq > 7) __syncthreads();  // ownership changes from phase A blocks to phase B sets
+        if (ph < ph_last) {
+            // a CTA barrier where the next stage reads elements another warp wrote: into / out of a CTA-wide stage, and
+            // where ownership changes from phase A blocks to phase B sets; otherwise the warp only waits for itself
+            const bool cta = v2_cta_stage<FLAGS>(ph, lq) || v2_cta_stage<FLAGS>(ph + 1, lq) || (ph == 7 && lq > 7);
+            if (cta) __syncthreads();
             else __syncwarp();
         }
-        cur = nxt;
-        ph = nph;
-        it = nit;
     }
     __syncwarp();
 

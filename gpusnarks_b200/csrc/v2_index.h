@@ -12,10 +12,10 @@
 
 namespace gsn {
 
-// Shared-memory slot of tile element e.  XOR-ing the low three bits with the next three keeps
-// eight consecutive elements on eight distinct 16-byte bank groups (the common case) and also
-// makes the stride-2, stride-4 and stride-8 element patterns of the early stages conflict free.
-GSN_HD uint32_t slot_of(uint32_t e) { return e ^ ((e >> 3) & 7u); }
+// Shared-memory slot of tile element e.  XOR-ing the low three bits with bits 3..5 and bits 6..8 keeps eight consecutive
+// elements on eight distinct 16-byte bank groups (the common case) and also makes the stride-2, -4, -8 and -16 element
+// patterns of the twiddle-major early stages conflict free (round 1 mixed in bits 3..5 only: stride 16 was 2-way).
+GSN_HD uint32_t slot_of(uint32_t e) { return e ^ (((e >> 3) ^ (e >> 6)) & 7u); }
 
 // Tile = 1024 element positions, 8 warps.  Element i (< 128) owned by warp W:
 //   phase A  (stages 1..7):   128 consecutive positions
@@ -41,6 +41,13 @@ GSN_HD void v2_butterfly(uint32_t W, uint32_t ph, uint32_t bl, uint32_t &lo, uin
         lo = (h << 7) | (W << 4) | l;
         jj = lo & (m - 1);
     }
+}
+// CTA-wide twiddle-major enumeration of stage ph (hybrid variant, stages 3 and 4): butterfly b (< 512) of the tile.
+// jj = b >> (10 - ph) is constant over 128 / 64 consecutive b, i.e. over whole warps: the jj == 0 warps skip the product.
+GSN_HD void cta_butterfly(uint32_t ph, uint32_t b, uint32_t &lo, uint32_t &jj) {
+    jj = b >> (10 - ph);
+    const uint32_t grp = b & ((1u << (10 - ph)) - 1);
+    lo = (grp << ph) | jj;
 }
 // iteration `it` of stage ph skips the product (all its twiddles are 1)
 GSN_HD bool v2_unit(uint32_t ph, uint32_t it) { return ph == 1 || (ph == 2 && it == 0); }

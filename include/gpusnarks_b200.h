@@ -67,8 +67,8 @@ int gsn_set_field768(gsn_ctx *ctx, int field);
  * the boundary's sub-problem, one product per element) larger than this is replaced by two-level tables of
  * 2 * sqrt(n) entries and two products per element -- 2^26 needs 3 MB instead of 13 GB.  GSN_OPT_PLAN_CACHE_BYTES
  * (default 16 GiB, and at most 16 plans): least-recently-used plans are dropped beyond it.  GSN_OPT_KERNEL_VARIANT:
- * kernel used for 1024-element tiles: 4 (or -1, default) = CTA-wide stages, 1 = warp-owned tiles with wide lazy ranges,
- * 3 = the same with twiddle prefetch (see DESIGN.md for the measurements). */
+ * kernel used for 1024-element tiles: 4 (or -1) = CTA-wide stages, 1 = warp-owned tiles with wide lazy ranges,
+ * 5 = the same with stages 3-4 enumerated CTA-wide (see DESIGN.md for the measurements). */
 #define GSN_OPT_FLAT_TABLE_LIMIT 1
 #define GSN_OPT_PLAN_CACHE_BYTES 2
 #define GSN_OPT_KERNEL_VARIANT 3

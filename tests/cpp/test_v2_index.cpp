@@ -23,7 +23,7 @@ static uint32_t brev(uint32_t x, uint32_t bits) { uint32_t r = 0; for (uint32_t 
 
 #define CHECK(c) do { if (!(c)) { printf("FAILED %s:%d: %s (lq=%u)\n", __FILE__, __LINE__, #c, lq); return 1; } } while (0)
 
-static int run(uint32_t lq, std::mt19937 &rng) {
+static int run(uint32_t lq, std::mt19937 &rng, bool hybrid) {
     const uint32_t T = 1024, L = 1u << lq;
     const uint64_t wL = powm(31, (P - 1) >> lq);  // primitive 2^lq-th root
     // tile input: T/L sub-transforms, natural order x[slot][j]; the kernel places element j at position brev(j)
@@ -70,16 +70,61 @@ static int run(uint32_t lq, std::mt19937 &rng) {
         }
         return 0;
     };
+    // hybrid variant: stage ph (3 or 4) enumerated CTA-wide and twiddle-major; the 8 warps are replayed in a random order
+    auto run_stage_cta = [&](uint32_t ph, std::vector<int> &touched, std::vector<uint32_t> worder) -> int {
+        for (uint32_t W : worder)
+            for (uint32_t it = 0; it < 2; ++it) {
+                uint32_t jj_warp = ~0u;
+                for (uint32_t half = 0; half < 2; ++half)
+                    for (uint32_t qw = 0; qw < 4; ++qw) {
+                        std::set<uint32_t> groups;
+                        for (uint32_t l8 = 0; l8 < 8; ++l8) {
+                            uint32_t lo, jj;
+                            gsn::cta_butterfly(ph, (W * 32 + qw * 8 + l8) + 256 * it, lo, jj);
+                            groups.insert((gsn::slot_of(half ? lo + (1u << (ph - 1)) : lo) * 7) & 7);
+                        }
+                        CHECK(groups.size() == 8);
+                    }
+                for (uint32_t lane = 0; lane < 32; ++lane) {
+                    uint32_t lo, jj;
+                    gsn::cta_butterfly(ph, (W * 32 + lane) + 256 * it, lo, jj);
+                    const uint32_t m = 1u << (ph - 1), hi = lo + m;
+                    if (jj_warp == ~0u) jj_warp = jj;
+                    CHECK(jj == jj_warp);   // warp uniform: a jj == 0 warp skips the product as a whole
+                    CHECK(hi < T && jj < m && (lo & m) == 0 && (lo & (m - 1)) == jj);
+                    touched[lo]++; touched[hi]++;
+                    const uint64_t w = powm(wL, (uint64_t)jj << (lq - ph));
+                    const uint64_t u = smem[lo], t = jj == 0 ? smem[hi] : mulm(smem[hi], w);
+                    smem[lo] = (u + t) % P;
+                    smem[hi] = (u + P - t) % P;
+                }
+            }
+        return 0;
+    };
     std::vector<uint32_t> order = {0, 1, 2, 3, 4, 5, 6, 7};
     // phase A: each warp runs ALL its phase-A stages before the next warp starts (no cross-warp sync exists there)
     std::shuffle(order.begin(), order.end(), rng);
     const uint32_t endA = std::min(lq, 7u);
     std::vector<std::vector<int>> touched(lq + 1, std::vector<int>(T, 0));
-    for (uint32_t W : order) {
-        std::set<uint32_t> owned;
-        for (uint32_t i = 0; i < 128; ++i) owned.insert(gsn::own_a(W, i));
-        CHECK(owned.size() == 128);
-        for (uint32_t ph = 1; ph <= endA; ++ph) if (run_stage_warp(W, ph, owned, touched[ph])) return 1;
+    auto phase_a = [&](uint32_t from, uint32_t to) -> int {
+        std::shuffle(order.begin(), order.end(), rng);
+        for (uint32_t W : order) {
+            std::set<uint32_t> owned;
+            for (uint32_t i = 0; i < 128; ++i) owned.insert(gsn::own_a(W, i));
+            CHECK(owned.size() == 128);
+            for (uint32_t ph = from; ph <= to; ++ph) if (run_stage_warp(W, ph, owned, touched[ph])) return 1;
+        }
+        return 0;
+    };
+    if (!hybrid) {
+        if (phase_a(1, endA)) return 1;
+    } else {   // stages 1-2 per warp | barrier | stage 3 CTA-wide | barrier | stage 4 CTA-wide | barrier | stages 5-7 per warp
+        if (phase_a(1, std::min(endA, 2u))) return 1;
+        for (uint32_t ph = 3; ph <= std::min(lq, 4u); ++ph) {
+            std::shuffle(order.begin(), order.end(), rng);
+            if (run_stage_cta(ph, touched[ph], order)) return 1;
+        }
+        if (endA >= 5 && phase_a(5, endA)) return 1;
     }
     // __syncthreads, then phase B the same way
     std::shuffle(order.begin(), order.end(), rng);
@@ -103,11 +148,33 @@ static int run(uint32_t lq, std::mt19937 &rng) {
     return 0;
 }
 
+// bank groups of the CTA-wide kernel's enumeration (ntt768_pass, 1024-element tile, 256 threads): twiddle-major in stages
+// 2..4, twiddle-minor elsewhere; every quarter warp of an LDS.128 / STS.128 must touch 8 distinct 16-byte groups
+static int check_cta_wide_kernel_banks() {
+    const uint32_t lq = 10;
+    for (uint32_t ph = 1; ph <= 10; ++ph)
+        for (uint32_t b0 = 0; b0 < 512; b0 += 8)
+            for (uint32_t half = 0; half < 2; ++half) {
+                std::set<uint32_t> groups;
+                for (uint32_t l8 = 0; l8 < 8; ++l8) {
+                    const uint32_t b = b0 + l8, m = 1u << (ph - 1);
+                    uint32_t jj, grp;
+                    if (ph >= 2 && ph <= 4) { jj = b >> (10 - ph); grp = b & ((1u << (10 - ph)) - 1); }
+                    else { jj = b & (m - 1); grp = b >> (ph - 1); }
+                    const uint32_t lo = (grp << ph) | jj;
+                    groups.insert((gsn::slot_of(half ? lo + m : lo) * 7) & 7);
+                }
+                CHECK(groups.size() == 8);
+            }
+    return 0;
+}
+
 int main() {
     std::mt19937 rng(12345);
+    if (check_cta_wide_kernel_banks()) return 1;
     for (int rep = 0; rep < 3; ++rep)
         for (uint32_t lq = 1; lq <= 10; ++lq)
-            if (run(lq, rng)) return 1;
-    printf("test_v2_index: ok (ownership, enumeration, unit iterations, bank groups, DFT parity for lq = 1..10)\n");
+            if (run(lq, rng, false) || run(lq, rng, true)) return 1;
+    printf("test_v2_index: ok (ownership, enumeration, unit iterations, bank groups, DFT parity for lq = 1..10, warp-owned and hybrid schedules)\n");
     return 0;
 }

@@ -27,10 +27,10 @@ def fresh():
     c.close()
 
 
-@pytest.mark.parametrize("variant", [-1, 1, 3, 4])
+@pytest.mark.parametrize("variant", [-1, 1, 5, 4])
 def test_kernel_variants_full_parity(fresh, variant):
-    """every variant of the 768-bit pass kernel (CTA-wide kernel; warp-owned tiles with lazy ranges, with / without
-    prefetch) gives the oracle's bits: 2^18 (two passes of 9 stages: phase B of the warp-owned scheme) and 2^20"""
+    """every variant of the 768-bit pass kernel (CTA-wide kernel; warp-owned tiles with lazy ranges, without / with
+    the CTA-wide stages 3-4) gives the oracle's bits: 2^18 (two passes of 9 stages: phase B of the warp-owned scheme) and 2^20"""
     fresh.set_option("kernel_variant", variant)
     for logn in (18, 20):
         n = 1 << logn
@@ -41,9 +41,12 @@ def test_kernel_variants_full_parity(fresh, variant):
         assert (fresh.ntt768(fwd, w, inverse=True) == a).all(), (variant, logn)
 
 
-@pytest.mark.parametrize("logn,batch", [(3, 1 << 15), (7, 1 << 12), (8, 1 << 11), (9, 1 << 10), (10, 1 << 9), (12, 256), (15, 32), (21, 1)])
-def test_large_tile_kernel_geometries(fresh, logn, batch):
-    """digit widths 3..10 in 1024-element tiles (several sub-transforms per tile, phase A only / phase A + B), batched"""
+@pytest.mark.parametrize("variant", [1, 5, 4])
+@pytest.mark.parametrize("logn,batch", [(1, 1 << 18), (3, 1 << 15), (4, 1 << 14), (7, 1 << 12), (8, 1 << 11), (9, 1 << 10), (10, 1 << 9), (12, 256), (15, 32), (21, 1)])
+def test_large_tile_kernel_geometries(fresh, logn, batch, variant):
+    """digit widths 1..10 in 1024-element tiles (several sub-transforms per tile, phase A only / phase A + B, with and
+    without the CTA-wide stages 3-4), batched, for each kernel that handles 1024-element tiles"""
+    fresh.set_option("kernel_variant", variant)
     n = 1 << logn
     a = fieldgen.random_elements(n * batch, 4300 + logn)
     w = fieldgen.omega768(n)

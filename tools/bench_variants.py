@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """A/B timing of the 768-bit pass-kernel variants on one GPU (device resident, CUDA events inside the library):
-variant 4 = CTA-wide kernel (round-1 structure: one barrier per stage, strict ranges), 5 = the same with wide lazy
-ranges, 0..3 = warp-owned large-tile kernel with flag bits 1 (wide lazy ranges) and 2 (twiddle prefetch).  Also flat vs two-level boundary tables.
+variant 4 = CTA-wide kernel (round-1 structure: one barrier per stage, strict ranges), 1 = warp-owned tiles with wide
+lazy ranges, 5 = the same with stages 3-4 enumerated CTA-wide (unit-twiddle skips).  Also flat vs two-level boundary tables.
 usage: python tools/bench_variants.py [LOGN ...]   -> one JSON line per (size, variant) on stdout"""
 import json
 import os
@@ -24,7 +24,7 @@ def main():
         a = rng.integers(0, 1 << 32, size=(n, 24), dtype=np.uint64).astype(np.uint32)
         a[:, 23] &= 0xFFFF
         ref = None
-        for variant, limit in [(4, None), (1, None), (3, None), (4, 1 << 16), (1, 1 << 16)]:
+        for variant, limit in [(4, None), (1, None), (5, None), (4, 1 << 16), (5, 1 << 16)]:
             ctx = g.Context(0)
             ctx.set_option("kernel_variant", variant)
             if limit:

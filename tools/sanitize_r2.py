@@ -40,7 +40,7 @@ def main():
     ctx = g.Context(0)
     for n, batch in ((1 << 10, 512), (1 << 8, 2048), (1 << 19, 1)):
         ref = run(ctx, n, batch, 4)
-        for variant, limit in ((1, None), (3, None), (1, 1 << 12)):
+        for variant, limit in ((1, None), (5, None), (5, 1 << 12)):
             assert (run(ctx, n, batch, variant, limit) == ref).all(), (n, variant, limit)
     ctx.set_option("kernel_variant", 1)
     ctx.trim()
