@@ -240,6 +240,37 @@ print(json.dumps({"import_ms": (t1 - t0) * 1e3, "ctx_create_ms": (t2 - t1) * 1e3
 """
 
 
+_ALL_CPUS = os.sched_getaffinity(0)
+
+
+def unbind_cpus():
+    """the CPU legs (reference arm, oracle spot checks) run on every core of the box again"""
+    try:
+        os.sched_setaffinity(0, _ALL_CPUS)
+    except Exception:
+        pass
+
+
+def bind_to_gpu_numa_node(gpu_index):
+    """pin this process to the CPU cores NVML reports as local to its GPU BEFORE any pinned host memory is allocated
+    (first touch then places the staging buffers on the GPU's NUMA node); with eight ranks copying at once the
+    end-to-end path is bound by host memory placement, not by the transforms.  Returns the number of cores, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def peaks_file():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -419,6 +450,7 @@ def run_single(args, torch, g, F, ctx, dev, stream, logn, config, rates):
     except Exception as e:
         secondary["ntt32_cfg2"] = {"error": str(e)}
     line["secondary"] = secondary
+    unbind_cpus()
     try:
         line["cpu_baseline"] = cpu_reference_run(min(args.cpu_sample_log_n, logn), 1, 0)
     except Exception as e:  # the bench line must still print
@@ -462,6 +494,7 @@ def sharded_parity(torch, dist, ctx, F, plan, y, logn, omega, rank, world, dev, 
         # Horner spot checks on the CPU oracle; the number of indices is sized to a time budget
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib as O
+        unbind_cpus()
         O.lib().oracle_set_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1; the other ranks are idle here
         cal_n = 1 << 16
         cal = np.ascontiguousarray(a[:cal_n].cpu().numpy().view(np.uint32))
@@ -736,6 +769,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert world == N or world == 1, f"--gpus {N} but WORLD_SIZE={world}"
 
+    numa_cores = bind_to_gpu_numa_node(local_rank)
+    config["host_affinity"] = f"process bound to the {numa_cores} cores local to its GPU (NVML)" if numa_cores else "not bound"
     ctx = g.Context(local_rank)
     stream = torch.cuda.Stream(dev)  # a real (non-default) stream: the library launches on it, torch events time it
     torch.cuda.set_stream(stream)

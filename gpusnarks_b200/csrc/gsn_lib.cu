@@ -535,7 +535,7 @@ int launch_ntt768_range(gsn_ctx *ctx, Plan768 *pl, uint32_t *d_data, size_t batc
         const unsigned grid = (unsigned)(ntiles ? ntiles : (total >> log_tile));
         const gsn::ScatterDesc &sc = (scatter && q + 1 == P) ? *scatter : no_scatter;
         const uint32_t *wloc = (const uint32_t *)pl->wloc.p;
-        if (log_tile == 10 && g.log_l >= 1 && (variant < 4 || g.wait_flags)) {   // a pass that waits on arrival flags needs the warp-owned kernel
+        if (log_tile == 10 && g.log_l >= 1 && (variant != 4 || g.wait_flags)) {   // a pass that waits on arrival flags needs the warp-owned kernel
             if (variant == 1) rc = launch_pass2<1>(ctx, grid, smem, st, src, dst, wloc, g, pd, post, sc);
             else rc = launch_pass2<5>(ctx, grid, smem, st, src, dst, wloc, g, pd, post, sc);   // variant 5, and every pass that waits on arrival flags
             if (rc) return rc;
