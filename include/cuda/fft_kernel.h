@@ -31,14 +31,18 @@ namespace gsn {
 inline void check(int rc, const char *what) {
     if (rc != GSN_OK) throw std::runtime_error(std::string(what) + ": " + gsn_last_error());
 }
-// one process-wide context per device for the template entry points (created once, thread safe)
-inline gsn_ctx *default_ctx(int device = 0) {
-    static gsn_ctx *ctx[16] = {nullptr};
+// one process-wide context per (device, 768-bit field) for the template entry points (created once, thread safe;
+// the field is a property of the context, so the Fr and the Fq context of a device never disturb each other)
+inline gsn_ctx *default_ctx(int device = 0, int field = GSN_FIELD_MNT4753_FR) {
+    static gsn_ctx *ctx[16][2] = {{nullptr}};
     static std::mutex mu;
-    if (device < 0 || device >= 16) throw std::runtime_error("gsn::default_ctx: device out of range");
+    if (device < 0 || device >= 16 || field < 0 || field > 1) throw std::runtime_error("gsn::default_ctx: device / field out of range");
     std::lock_guard<std::mutex> lk(mu);
-    if (!ctx[device]) check(gsn_ctx_create(&ctx[device], device), "gsn_ctx_create");
-    return ctx[device];
+    if (!ctx[device][field]) {
+        check(gsn_ctx_create(&ctx[device][field], device), "gsn_ctx_create");
+        if (field != GSN_FIELD_MNT4753_FR) check(gsn_set_field768(ctx[device][field], field), "gsn_set_field768");
+    }
+    return ctx[device][field];
 }
 // Transforms of 2^24 elements and more are sharded over every visible GPU (1, 2, 4 or 8 of them; the four-step plan of
 // gsn_multi_*, peer access between the devices of this one process).  GSN_MULTI_MIN_LOG_N overrides the threshold,
@@ -85,7 +89,9 @@ template <> struct fft_dispatch<fields::Scalar> {
 template <> struct fft_dispatch<cpu_fields::Field> {
     static void run(std::vector<cpu_fields::Field> &a, const cpu_fields::Field &omg, int inverse) {
         static_assert(sizeof(cpu_fields::Field) == 96, "raw limbs");
-        check(gsn_ntt768_host(default_ctx(), reinterpret_cast<uint32_t *>(a.data()), a.size(), omg.im_rep, inverse), "gsn_ntt768_host");
+        // cpu_fields::Field follows the host-side modulus selection (cpu_fields::modulus().select(0 = Fr | 1 = Fq))
+        const int field = cpu_fields::modulus().which ? GSN_FIELD_MNT4753_FQ : GSN_FIELD_MNT4753_FR;
+        check(gsn_ntt768_host(default_ctx(0, field), reinterpret_cast<uint32_t *>(a.data()), a.size(), omg.im_rep, inverse), "gsn_ntt768_host");
     }
 };
 template <> struct fft_dispatch<dummy_fields::Field> {

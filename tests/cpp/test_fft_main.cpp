@@ -84,12 +84,37 @@ static int test_fft32(size_t log_n) {
     return 0;
 }
 
+// cpu_fields::Field over the reference's literal modulus (MNT4-753 Fq, 2-adicity 15): the shim must follow the host-side
+// modulus selection and use a context of that field
+static int test_fft768_fq(size_t log_n) {
+    printf("\nTEST FFT (768-bit, cpu_fields::Field over MNT4-753 Fq), 2^%zu\n", log_n);
+    cpu_fields::modulus().select(1);
+    const size_t _size = (size_t)1 << log_n;
+    std::vector<cpu_fields::Field> v1, v2;
+    std::mt19937_64 rng(2);
+    for (size_t i = 0; i < _size; i++) {
+        uint32_t limbs[SIZE];
+        for (int k = 0; k < SIZE; ++k) limbs[k] = (uint32_t)rng();
+        limbs[SIZE - 1] &= 0xFFFF;
+        v1.push_back(cpu_fields::Field(limbs));
+        v2.push_back(cpu_fields::Field(limbs));
+    }
+    const cpu_fields::Field omega = cpu_fields::Field::root_of_unity(_size);
+    best_fft<cpu_fields::Field>(v1, omega);
+    oracle::_basic_parallel_radix2_FFT_inner<cpu_fields::Field>(v2, omega, 3, cpu_fields::Field::one());
+    cpu_fields::modulus().select(0);
+    if (!(v1 == v2)) { printf("FQ MISMATCH\n"); return 1; }
+    printf("forward == host FFT over Fq, DONE\n");
+    return 0;
+}
+
 int main(int argc, char **argv) {
     const size_t l768 = argc > 1 ? (size_t)atoi(argv[1]) : 16;  // the reference's shape: 1 << 16
     const size_t l32 = argc > 2 ? (size_t)atoi(argv[2]) : 16;
     try {
         if (test_fft768(l768)) return 1;
         if (test_fft32(l32)) return 1;
+        if (test_fft768_fq(12)) return 1;
     } catch (const std::exception &e) {
         printf("ERROR: %s\n", e.what());
         return 2;

@@ -60,7 +60,7 @@ def test_cpp_drop_in_driver_runs():
                                "-lgpusnarks_b200", "-Wl,-rpath," + os.path.join(ROOT, "gpusnarks_b200")])
     out = subprocess.run([exe, "16", "20"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert out.stdout.count("DONE") == 2 and "MISMATCH" not in out.stdout and "Missmatch" not in out.stdout
+    assert out.stdout.count("DONE") == 3 and "MISMATCH" not in out.stdout and "Missmatch" not in out.stdout
 
 
 def test_cpp_best_fft_shards_over_the_visible_gpus():
@@ -73,4 +73,4 @@ def test_cpp_best_fft_shards_over_the_visible_gpus():
     env = dict(os.environ, GSN_MULTI_MIN_LOG_N="18")
     out = subprocess.run([exe, "18", "16"], capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert out.stdout.count("DONE") == 2 and "MISMATCH" not in out.stdout and "Missmatch" not in out.stdout
+    assert out.stdout.count("DONE") == 3 and "MISMATCH" not in out.stdout and "Missmatch" not in out.stdout
