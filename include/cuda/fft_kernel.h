@@ -69,7 +69,10 @@ inline gsn_multi *default_multi(size_t n, const uint32_t *omega) {
     Entry ent;
     ent.n = n;
     std::memcpy(ent.omega, omega, sizeof(ent.omega));
-    check(gsn_multi_create(&ent.m, ids, (unsigned)devices, n, omega, 3), "gsn_multi_create");
+    if (gsn_multi_create(&ent.m, ids, (unsigned)devices, n, omega, 3) != GSN_OK) {
+        devices = 1;   // e.g. no peer access between the devices: keep to the single-GPU path from now on
+        return nullptr;
+    }
     if (cache.size() >= 2) { gsn_multi_destroy(cache.front().m); cache.erase(cache.begin()); }
     cache.push_back(ent);
     return ent.m;
