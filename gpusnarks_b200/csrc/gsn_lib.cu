@@ -943,17 +943,12 @@ int gsn_fp768_powers_device(gsn_ctx *ctx, uint32_t *d_table, size_t count, const
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-    DevBuf d_bs;
-    int rc;
-    if ((rc = dev_alloc(d_bs, 192))) return rc;
-    uint32_t h[48];
-    memcpy(h, base, 96);
-    memcpy(h + 24, scale ? scale : ctx->fc.r1, 96);
-    CU(cudaMemcpyAsync(d_bs.p, h, 192, cudaMemcpyHostToDevice, st));
-    gsn::powers768<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(ctx->fc, d_table, (const uint32_t *)d_bs.p, (const uint32_t *)d_bs.p + 24, count);
+    gsn::Elem768 b, sc;   // by value in the launch parameters: stream ordered, nothing to allocate or wait for
+    memcpy(b.v, base, 96);
+    memcpy(sc.v, scale ? scale : ctx->fc.r1, 96);
+    gsn::powers768<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(ctx->fc, d_table, b, sc, count);
     ctx->launches++;
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(st));  // d_bs is freed on return
     return GSN_OK;
 }
 

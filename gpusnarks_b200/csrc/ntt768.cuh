@@ -539,12 +539,15 @@ __global__ void scale_table768(const __grid_constant__ FieldConstants768 fc, uin
 
 // out[i] = scale * base^i (canonical), i < count: coset shifts g^i for coset transforms.
 // Thread i computes base^i by square-and-multiply (tables are built once per domain).
-__global__ void powers768(const __grid_constant__ FieldConstants768 fc, uint32_t *out, const uint32_t *base, const uint32_t *scale, uint64_t count) {
+struct Elem768 { uint32_t v[NL]; };   // one field element by value (kernel parameter: no device allocation, no copy to wait for)
+
+__global__ void powers768(const __grid_constant__ FieldConstants768 fc, uint32_t *out, const __grid_constant__ Elem768 base,
+                          const __grid_constant__ Elem768 scale, uint64_t count) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     uint32_t b[NL], acc[NL];
-    load_elem(b, base);
-    load_elem(acc, scale);
+#pragma unroll
+    for (int k = 0; k < NL; ++k) { b[k] = base.v[k]; acc[k] = scale.v[k]; }
     const int top = 63 - __clzll((long long)(i | 1));
     uint32_t r[NL];
 #pragma unroll
