@@ -203,19 +203,29 @@ __device__ __forceinline__ void mont_mul(GSN_FC, uint32_t *r, const uint32_t *a,
 // Row primitive: adds sum_{j in [jlo, jhi)} a[j] * b * 2^(32 (i + j)) into the interleaved accumulators (EV: products
 // starting on an even limb position, OD: odd, shifted by one limb), positions relative to BASE; positions >= TOP fall
 // outside the kept range (their carries are dropped) and at position LO_POS only the low word is kept.
-template <int BASE, int TOP, int LO_POS>
+// FRESH_TOP: the chain that ends with the product a[NL-1] * b (limb position i + NL - 1) propagates no carry: that
+// register pair is touched by no earlier product of the row sequence i = 0, 1, 2, ... and holds at most a propagated
+// carry bit in its low limb, so lo + product + carry-in < 2^64 (asserted limb for limb in tools/model_products.py).
+// FIRST_ROW: the accumulators hold nothing yet: every product is WRITTEN (mul.lo / mul.hi, no carry chain, and no
+// zero-initialisation of the accumulators before it).
+template <int BASE, int TOP, int LO_POS, bool FRESH_TOP = false, bool FIRST_ROW = false>
 __device__ __forceinline__ void row_mac(uint32_t *ev, uint32_t *od, const uint32_t *a, uint32_t b, int i, int jlo, int jhi) {
 #pragma unroll
     for (int parity = 0; parity < 2; ++parity) {
         uint32_t *arr = parity ? od : ev;
         bool started = false;
-        int last = -1;
+        int last = -1, last_j = -1;
 #pragma unroll
         for (int j = 0; j < NL; ++j) {
             if (j < jlo || j >= jhi) continue;
             const int pos = i + j;
             if ((pos & 1) != parity) continue;
             const int k = pos - BASE - parity;
+            if (FIRST_ROW) {
+                if (pos == LO_POS) arr[k] = a[j] * b;
+                else mul_wide(arr[k], arr[k + 1], a[j], b);
+                continue;
+            }
             if (pos == LO_POS) {  // only the low word lands inside the kept range; it ends the chain
                 if (started) asm volatile("madc.lo.u32 %0, %1, %2, %0;" : "+r"(arr[k]) : "r"(a[j]), "r"(b));
                 else asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(arr[k]) : "r"(a[j]), "r"(b));
@@ -226,9 +236,10 @@ __device__ __forceinline__ void row_mac(uint32_t *ev, uint32_t *od, const uint32
                 else madc_wide_cc(arr[k], arr[k + 1], a[j], b);
                 started = true;
                 last = k + 1;
+                last_j = j;
             }
         }
-        if (started && (BASE + last + 1 + parity) < TOP) arr[last + 1] = addc(arr[last + 1], 0u);
+        if (started && (BASE + last + 1 + parity) < TOP && !(FRESH_TOP && last_j == NL - 1)) arr[last + 1] = addc(arr[last + 1], 0u);
     }
 }
 // out[k] = EV[k] + OD[k-1] (+ carry), k < N
@@ -244,10 +255,10 @@ __device__ __forceinline__ void merge_evod(uint32_t *out, const uint32_t *ev, co
 template <typename BWord>
 __device__ __forceinline__ void mul_lo768(uint32_t *r, const uint32_t *a, BWord b) {
     uint32_t ev[NL + 2], od[NL + 2];
+    // row 0 covers limb positions 0..23, i.e. every accumulator limb merge_evod<NL> reads: it writes them, nothing is zeroed
+    row_mac<0, NL, NL - 1, false, true>(ev, od, a, b(0), 0, 0, NL);
 #pragma unroll
-    for (int k = 0; k < NL + 2; ++k) ev[k] = od[k] = 0;
-#pragma unroll
-    for (int i = 0; i < NL; ++i) row_mac<0, NL, NL - 1>(ev, od, a, b(i), i, 0, NL - i);
+    for (int i = 1; i < NL; ++i) row_mac<0, NL, NL - 1>(ev, od, a, b(i), i, 0, NL - i);
     merge_evod<NL>(r, ev, od);
 }
 struct ConstModulus { const FieldConstants768 &fc; __device__ __forceinline__ uint32_t operator()(int i) const { return fc.p[i]; } };
@@ -274,7 +285,7 @@ __device__ __forceinline__ void shoup_mul_3p(GSN_FC, uint32_t *t, XWords x1, XWo
 #pragma unroll
         for (int k = 0; k < NL + 4; ++k) ev[k] = od[k] = 0;
 #pragma unroll
-        for (int i = 0; i < NL; ++i) row_mac<22, 1000, -1>(ev, od, w2, x1(i), i, (22 - i) > 0 ? (22 - i) : 0, NL);
+        for (int i = 0; i < NL; ++i) row_mac<22, 1000, -1, true>(ev, od, w2, x1(i), i, (22 - i) > 0 ? (22 - i) : 0, NL);
         merge_evod<NL + 2>(hi, ev, od);  // limbs 22..47 of x * w''
 #pragma unroll
         for (int k = 0; k < NL; ++k) q[k] = hi[k + 2];

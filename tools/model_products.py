@@ -110,10 +110,13 @@ class _Acc:
         self.ev = [0] * (size + 2)
         self.od = [0] * (size + 2)
 
-    def row(self, a, b, i, jlo, jhi, lo_pos=None, top=None):
+    def row(self, a, b, i, jlo, jhi, lo_pos=None, top=None, fresh_top=False):
+        """fresh_top: the device code drops the carry propagation after a chain whose last link is the product a[NL-1]*b
+        (limb position i + NL - 1): that (even/odd) register pair is touched by no earlier product and holds at most a
+        propagated carry bit in its low limb, so lo + product + carry-in < 2^64 and the link cannot carry out."""
         for parity in (0, 1):
             arr = self.ev if parity == 0 else self.od
-            carry, last = 0, None
+            carry, last, last_j = 0, None, None
             for j in range(jlo, jhi):
                 pos = i + j
                 if pos % 2 != parity:
@@ -127,7 +130,10 @@ class _Acc:
                     continue
                 s = arr[k + 1] + (prod >> 32) + carry
                 arr[k + 1], carry = s & M32, s >> 32
-                last = k + 1
+                last, last_j = k + 1, j
+            if fresh_top and last is not None and last_j == NL - 1:
+                assert carry == 0, "the top link of a row carried out"
+                continue
             if last is not None and carry and (top is None or self.base + last + 1 + parity < top):
                 s = arr[last + 1] + carry
                 assert s >> 32 == 0
@@ -154,7 +160,7 @@ def shoup_mul(x, w, p):
     X, W, W2, P = limbs(x), limbs(w), limbs((w * R) // p), limbs(p)
     acc = _Acc(22, NL + 4)
     for i in range(NL):
-        acc.row(W2, X[i], i, max(0, 22 - i), NL)
+        acc.row(W2, X[i], i, max(0, 22 - i), NL, fresh_top=True)
     q = acc.merge(NL + 2)[2:]
     t = (val(mul_lo768(W, X)) - val(mul_lo768(q, P))) % R
     if t >= 2 * p:
@@ -167,7 +173,7 @@ def shoup_mul_3p(x, w, p):
     X, W, W2, P = limbs(x), limbs(w), limbs((w * R) // p), limbs(p)
     acc = _Acc(22, NL + 4)
     for i in range(NL):
-        acc.row(W2, X[i], i, max(0, 22 - i), NL)
+        acc.row(W2, X[i], i, max(0, 22 - i), NL, fresh_top=True)
     q = acc.merge(NL + 2)[2:]
     return (val(mul_lo768(W, X)) - val(mul_lo768(q, P))) % R, val(q)
 
@@ -231,7 +237,7 @@ def self_check(p, cases=400, seed=1):
         wm = w * R % p
         assert shoup_constant_from_montgomery(wm, p) == (w * R) // p
         # wide lazy ranges: any x below 2^768 (not only below 2p) gives t in [0, 3p) and t = x*w mod p
-        xs = [R - 1, R - p, 36 * p, 64 * p - 1, rnd.randrange(R), rnd.randrange(36 * p)]
+        xs = [R - 1, R - p, 36 * p, 64 * p - 1, rnd.randrange(R), rnd.randrange(36 * p), R - (1 << 32), (R - 1) ^ ((1 << 384) - 1)]
         xl = xs[it % len(xs)]
         t3, q3 = shoup_mul_3p(xl, w, p)
         assert t3 < 3 * p and t3 % p == xl * w % p and 0 <= (xl * w) // p - q3 <= 2
