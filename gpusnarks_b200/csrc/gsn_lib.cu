@@ -1345,7 +1345,8 @@ int gsn_int32_issue_rates(gsn_ctx *ctx, double *rates, int max_modes, int *n_mod
     const int iters = 2048, blocks = ctx->sm_count * 8, threads = 256;
     typedef void (*launch_fn)(int, int, cudaStream_t, uint32_t *, const uint32_t *, int);
     static const launch_fn fns[gsn::INT32_PROBE_MODES] = {launch_probe<0>, launch_probe<1>, launch_probe<2>,
-                                                         launch_probe<3>, launch_probe<4>, launch_probe<5>};
+                                                         launch_probe<3>, launch_probe<4>, launch_probe<5>,
+                                                         launch_probe<6>, launch_probe<7>};
     const int modes = std::min(max_modes, gsn::INT32_PROBE_MODES);
     for (int mode = 0; mode < modes; ++mode) {
         float best = 1e30f;

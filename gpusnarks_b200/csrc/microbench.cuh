@@ -14,12 +14,14 @@
 //   MODE 3  IMAD.WIDE   same, one shared multiplicand pair (operand-reuse friendly)
 //   MODE 4  IMAD.WIDE.U32.X  carry chains of 8 links (the form the CIOS product issues)
 //   MODE 5  IADD3.X     add.cc / addc.cc chains of 8
+//   MODE 6  DFMA        fma.rz.f64, 16 independent accumulators (what a 52-bit-limb product would issue)
+//   MODE 7  IMAD.WIDE + DFMA interleaved 8 + 8: do the two pipes run side by side?
 #pragma once
 #include <cstdint>
 
 namespace gsn {
 
-constexpr int INT32_PROBE_MODES = 6;
+constexpr int INT32_PROBE_MODES = 8;
 constexpr int INT32_PROBE_UNROLL = 4;  // repetitions of the 8-accumulator group per loop iteration
 
 template <int MODE>
@@ -28,6 +30,13 @@ __global__ void __launch_bounds__(256) int32_issue_probe(uint32_t *sink, const u
     uint32_t b0 = in[threadIdx.x & 31], b1 = in[32 + (threadIdx.x & 31)];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { a[i] = in[64 + i + threadIdx.x]; lo[i] = a[i] * 3u + i; hi[i] = a[i] * 5u + i; }
+    double d[16], e[8];
+    if (MODE >= 6) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) d[i] = (double)(in[128 + i + threadIdx.x] & 0xFFFFF) * 1e-9;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) e[i] = 1.0 + (double)(a[i] & 0xFFFF) * 1e-12;
+    }
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int rep = 0; rep < INT32_PROBE_UNROLL; ++rep) {
@@ -58,6 +67,15 @@ __global__ void __launch_bounds__(256) int32_issue_probe(uint32_t *sink, const u
                 for (int i = 1; i < 8; ++i)
                     asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo[i]), "+r"(hi[i]) : "r"(a[i]), "r"(b));
                 asm volatile("addc.u32 %0, %0, 0;" : "+r"(b1));
+            } else if (MODE == 6) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) asm volatile("fma.rz.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(e[i & 7]), "d"(e[(i + rep) & 7]));
+            } else if (MODE == 7) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;" : "+r"(lo[i]), "+r"(hi[i]) : "r"(a[i]), "r"(b));
+                    asm volatile("fma.rz.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(e[i]), "d"(e[(i + rep) & 7]));
+                }
             } else {
                 asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(lo[0]) : "r"(a[0]));
 #pragma unroll
@@ -71,12 +89,16 @@ __global__ void __launch_bounds__(256) int32_issue_probe(uint32_t *sink, const u
     uint32_t x = b1;
 #pragma unroll
     for (int i = 0; i < 8; ++i) x ^= lo[i] ^ hi[i];
+    if (MODE >= 6) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x ^= (uint32_t)__double2hiint(d[i]) ^ (uint32_t)__double2loint(d[i]);
+    }
     if (x == 0x12345678u) sink[0] = x;  // never true in practice; keeps the work alive
 }
 
 // timed instructions per thread per loop iteration
 __host__ inline int int32_probe_ops_per_iter(int mode) {
-    return INT32_PROBE_UNROLL * ((mode == 0 || mode == 1 || mode == 5) ? 16 : 8);
+    return INT32_PROBE_UNROLL * ((mode == 0 || mode == 1 || mode == 5 || mode == 6 || mode == 7) ? 16 : 8);
 }
 
 }  // namespace gsn

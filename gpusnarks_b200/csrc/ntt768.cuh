@@ -21,7 +21,7 @@
 // All twiddle products of the kernel go through ONE inlined call site (the `ph` loop):
 // the product is ~1k instructions, and a single copy keeps the kernel inside the
 // instruction cache.  Butterflies whose twiddle is 1 skip the product: all of stage 1, and in
-// stages 2-4 the jj == 0 butterflies, which a twiddle-major enumeration packs into whole warps
+// stages 2-5 the jj == 0 butterflies, which a twiddle-major enumeration packs into whole warps
 // (about 10 % of the products of a 10-stage pass).
 //
 // Shared memory layout: AoS with a 112-byte pitch (96 B of limbs + 16 B pad).  With a
@@ -177,8 +177,8 @@ __device__ __forceinline__ void sts_elem(uint4 *s, const uint32_t *r) {
 
 // ------------------------------------------------------------------ CTA-wide kernel (any tile size)
 // CTA-wide enumeration of the butterflies of every stage, one __syncthreads per stage, values in [0, 2p) between stages.
-// Stages 2..4 are enumerated twiddle-major, so the butterflies with a unit twiddle fill whole warps and skip the
-// product (1.875 of 10 stages' worth).  (A wide-lazy-range form of this kernel measured 2 % slower and was removed.)
+// Stages 2..5 are enumerated twiddle-major, so the butterflies with a unit twiddle fill whole warps and skip the
+// product (1.9375 of 10 stages' worth).  (A wide-lazy-range form of this kernel measured 2 % slower and was removed.)
 template <int THREADS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 ntt768_pass(const uint32_t *src, uint32_t *dst, const uint32_t *__restrict__ wloc, const __grid_constant__ PassGeom g,
@@ -220,7 +220,7 @@ ntt768_pass(const uint32_t *src, uint32_t *dst, const uint32_t *__restrict__ wlo
             } else {
                 const uint32_t m = 1u << (ph - 1);
                 uint32_t jj, grp;
-                const bool twiddle_major = ph >= 2 && ph <= 4 && g.log_tile >= (uint32_t)ph + 5;
+                const bool twiddle_major = ph >= 2 && ph <= 5 && g.log_tile >= (uint32_t)ph + 5;
                 if (twiddle_major) {
                     // early stages: enumerate butterflies twiddle-major, so that the T/2m butterflies
                     // with jj == 0 (unit twiddle) fill whole warps and skip the product

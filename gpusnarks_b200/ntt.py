@@ -285,7 +285,8 @@ class Context:
         rates = (C.c_double * 16)()
         nm, sm, khz = C.c_int(), C.c_int(), C.c_int()
         self._check(self.L.gsn_int32_issue_rates(self._h, rates, 16, C.byref(nm), C.byref(sm), C.byref(khz)))
-        names = ["imad_lo", "imad_hi", "imad_wide", "imad_wide_shared_operands", "imad_wide_x_chain", "iadd3_x_chain"]
+        names = ["imad_lo", "imad_hi", "imad_wide", "imad_wide_shared_operands", "imad_wide_x_chain", "iadd3_x_chain", "dfma_f64",
+                 "imad_wide_plus_dfma_interleaved"]
         return {"rates": {names[k]: rates[k] for k in range(nm.value)}, "sm_count": sm.value, "sm_clock_khz": khz.value}
 
 

@@ -149,7 +149,7 @@ static int run(uint32_t lq, std::mt19937 &rng, bool hybrid) {
 }
 
 // bank groups of the CTA-wide kernel's enumeration (ntt768_pass, 1024-element tile, 256 threads): twiddle-major in stages
-// 2..4, twiddle-minor elsewhere; every quarter warp of an LDS.128 / STS.128 must touch 8 distinct 16-byte groups
+// 2..5, twiddle-minor elsewhere; every quarter warp of an LDS.128 / STS.128 must touch 8 distinct 16-byte groups
 static int check_cta_wide_kernel_banks() {
     const uint32_t lq = 10;
     for (uint32_t ph = 1; ph <= 10; ++ph)
@@ -159,7 +159,7 @@ static int check_cta_wide_kernel_banks() {
                 for (uint32_t l8 = 0; l8 < 8; ++l8) {
                     const uint32_t b = b0 + l8, m = 1u << (ph - 1);
                     uint32_t jj, grp;
-                    if (ph >= 2 && ph <= 4) { jj = b >> (10 - ph); grp = b & ((1u << (10 - ph)) - 1); }
+                    if (ph >= 2 && ph <= 5) { jj = b >> (10 - ph); grp = b & ((1u << (10 - ph)) - 1); }
                     else { jj = b & (m - 1); grp = b >> (ph - 1); }
                     const uint32_t lo = (grp << ph) | jj;
                     groups.insert((gsn::slot_of(half ? lo + m : lo) * 7) & 7);

@@ -94,3 +94,6 @@ def test_sass_is_what_the_design_claims(lib):
     assert _sass_histogram("int32_issue_probeILi4E").get("IMAD.WIDE.U32.X", 0) > 500
     assert _sass_histogram("int32_issue_probeILi0E").get("IMAD", 0) > 1000
     assert _sass_histogram("int32_issue_probeILi1E").get("IMAD.HI.U32", 0) > 1000
+    assert _sass_histogram("int32_issue_probeILi6E").get("DFMA.RZ", 0) >= 64
+    mixed = _sass_histogram("int32_issue_probeILi7E")
+    assert mixed.get("DFMA.RZ", 0) >= 32 and mixed.get("IMAD.WIDE.U32", 0) >= 32
