@@ -419,13 +419,18 @@ def run_single(args, torch, g, F, ctx, dev, stream, logn, config, rates):
                         "api": "gsn_ntt768_host_batch, 4 pinned vectors per call: H2D of vector i+1 overlaps passes and D2H of vector i"},
         "e2e_pageable": {"value": bf / (e2e_pageable_ms * 1e-3), "unit": "butterflies/s", "ms_per_step": e2e_pageable_ms,
                          "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                         "api": "gsn_ntt768_host on pageable memory (what best_fft(std::vector&) passes): pinned bounce buffers + threaded memcpy inside the call"},
+                         "api": "gsn_ntt768_host on pageable memory (what best_fft(std::vector&) passes): column blocks gathered into pinned bounce buffers by host threads, pipelined with the DMA and the passes"},
     }
     secondary = {}
     try:
-        out = subprocess.run([sys.executable, "-c", FIRST_CALL_SCRIPT % (ROOT, logn)], capture_output=True, text=True, timeout=180)
-        secondary["first_call"] = json.loads(out.stdout.strip().splitlines()[-1])
-        secondary["first_call"]["what"] = f"fresh process: gsn_ctx_create, then the first and second best_fft (2^{logn}, pageable vector); the first call builds the plan"
+        runs = []
+        for _ in range(2):   # two fresh processes: the very first one on a box also pays for cold page cache / driver state
+            out = subprocess.run([sys.executable, "-c", FIRST_CALL_SCRIPT % (ROOT, logn)], capture_output=True, text=True, timeout=180)
+            runs.append(json.loads(out.stdout.strip().splitlines()[-1]))
+        secondary["first_call"] = dict(min(runs, key=lambda r: r["first_call_ms"]))
+        secondary["first_call"]["all_runs_first_call_ms"] = [r["first_call_ms"] for r in runs]
+        secondary["first_call"]["what"] = (f"fresh process (best of 2): gsn_ctx_create, then the first and second best_fft (2^{logn}, pageable vector); "
+                                           "the first call builds the plan, the pinned bounce buffers and the host copy threads")
     except Exception as e:
         secondary["first_call"] = {"error": str(e)}
     try:

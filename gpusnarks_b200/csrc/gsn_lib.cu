@@ -10,10 +10,12 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -123,6 +125,61 @@ struct StreamWork {   // scratch buffer of the multi-pass transforms, one per st
 
 struct gsn_coset_entry;
 
+// A few persistent host threads that move data between a caller's pageable memory and the pinned bounce buffers
+// (run() blocks; the calling thread works as thread 0).
+struct HostPool {
+    std::vector<std::thread> threads;
+    std::mutex m;
+    std::condition_variable cv, done_cv;
+    const std::function<void(unsigned, unsigned)> *job = nullptr;
+    uint64_t epoch = 0;
+    unsigned pending = 0, nt = 1;
+    bool stop = false;
+    explicit HostPool(unsigned n) : nt(std::max(1u, n)) {
+        for (unsigned t = 1; t < nt; ++t)
+            threads.emplace_back([this, t] {
+                uint64_t seen = 0;
+                for (;;) {
+                    const std::function<void(unsigned, unsigned)> *fn;
+                    {
+                        std::unique_lock<std::mutex> lk(m);
+                        cv.wait(lk, [&] { return stop || epoch != seen; });
+                        if (stop) return;
+                        seen = epoch;
+                        fn = job;
+                    }
+                    (*fn)(t, nt);
+                    {
+                        std::lock_guard<std::mutex> lk(m);
+                        if (--pending == 0) done_cv.notify_one();
+                    }
+                }
+            });
+    }
+    ~HostPool() {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            stop = true;
+        }
+        cv.notify_all();
+        for (auto &t : threads) t.join();
+    }
+    void run(const std::function<void(unsigned, unsigned)> &fn) {
+        if (nt > 1) {
+            std::lock_guard<std::mutex> lk(m);
+            job = &fn;
+            pending = nt - 1;
+            ++epoch;
+        }
+        cv.notify_all();
+        fn(0, nt);
+        if (nt > 1) {
+            std::unique_lock<std::mutex> lk(m);
+            done_cv.wait(lk, [&] { return pending == 0; });
+        }
+    }
+};
+
 struct gsn_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -148,9 +205,11 @@ struct gsn_ctx {
     cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the pipelined host-pointer path
     cudaEvent_t ev_chunk[2][16] = {{nullptr}};
     std::unordered_set<const void *> smem_configured;  // kernels whose dynamic shared-memory limit was raised on this device
-    // pinned bounce buffers of the pageable host path
-    void *bounce[2] = {nullptr, nullptr};
+    // pinned bounce buffers of the pageable host path (two per direction) and the host threads that fill / drain them
+    void *bounce[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t bounce_bytes = 0;
+    cudaEvent_t ev_bounce[2] = {nullptr, nullptr};
+    std::unique_ptr<HostPool> pool;
     gsn_ctx();
     ~gsn_ctx();
 };
@@ -603,6 +662,7 @@ int gsn_ctx_create(gsn_ctx **out, int device) {
     for (int d = 0; d < 2; ++d)
         for (int i = 0; i < 16; ++i) CU(cudaEventCreateWithFlags(&ctx->ev_chunk[d][i], cudaEventDisableTiming));
     for (int d = 0; d < 2; ++d) CU(cudaEventCreateWithFlags(&ctx->ev_io_free[d], cudaEventDisableTiming));
+    for (int d = 0; d < 2; ++d) CU(cudaEventCreateWithFlags(&ctx->ev_bounce[d], cudaEventDisableTiming));
     int rc = set_field(ctx.get(), GSN_FIELD_MNT4753_FR);
     if (rc) return rc;
     if (const char *v = getenv("GSN_NTT768_VARIANT")) { const int k = atoi(v); if (k == -1 || k == 1 || k == 5 || k == 4) ctx->v2_flags = k; }
@@ -620,7 +680,9 @@ int gsn_ctx_destroy(gsn_ctx *ctx) {
     ctx->plans32.clear();
     ctx->cosets.clear();
     ctx->works.clear();
-    for (int b = 0; b < 2; ++b) if (ctx->bounce[b]) cudaFreeHost(ctx->bounce[b]);
+    ctx->pool.reset();
+    for (int b = 0; b < 4; ++b) if (ctx->bounce[b]) cudaFreeHost(ctx->bounce[b]);
+    for (int d = 0; d < 2; ++d) if (ctx->ev_bounce[d]) cudaEventDestroy(ctx->ev_bounce[d]);
     for (int d = 0; d < 2; ++d)
         for (int i = 0; i < 16; ++i) if (ctx->ev_chunk[d][i]) cudaEventDestroy(ctx->ev_chunk[d][i]);
     for (int d = 0; d < 2; ++d) if (ctx->ev_io_free[d]) cudaEventDestroy(ctx->ev_io_free[d]);
@@ -805,31 +867,107 @@ static bool is_pageable(const void *p) {
     return a.type == cudaMemoryTypeUnregistered;
 }
 
-static void parallel_memcpy(void *dst, const void *src, size_t bytes) {
-    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const size_t nt = std::max<size_t>(1, std::min<size_t>({(size_t)4, (size_t)hw, bytes >> 20}));
-    if (nt == 1) { memcpy(dst, src, bytes); return; }
-    const size_t per = ((bytes / nt) + 4095) & ~(size_t)4095;
-    std::vector<std::thread> ts;
-    for (size_t t = 1; t < nt; ++t) {
-        const size_t off = t * per, len = off >= bytes ? 0 : std::min(per, bytes - off);
-        if (len) ts.emplace_back([=] { memcpy((char *)dst + off, (const char *)src + off, len); });
+static HostPool &host_pool(gsn_ctx *ctx) {
+    if (!ctx->pool) {
+        unsigned nt = std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+        if (const char *v = getenv("GSN_HOST_THREADS")) nt = (unsigned)std::max(1, std::min(64, atoi(v)));
+        ctx->pool.reset(new HostPool(nt));
     }
-    memcpy(dst, src, std::min(per, bytes));
-    for (auto &t : ts) t.join();
+    return *ctx->pool;
+}
+
+// rows x width bytes between two pitched host buffers, rows split over the pool
+static void copy_rows(gsn_ctx *ctx, void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows) {
+    host_pool(ctx).run([=](unsigned t, unsigned nt) {
+        if (dpitch == width && spitch == width) {   // contiguous: split by bytes, page aligned
+            const size_t bytes = width * rows, per = ((bytes / nt) + 4095) & ~(size_t)4095;
+            const size_t off = t * per;
+            if (off < bytes) memcpy((char *)dst + off, (const char *)src + off, std::min(per, bytes - off));
+            return;
+        }
+        const size_t r0 = rows * t / nt, r1 = rows * (t + 1) / nt;
+        for (size_t r = r0; r < r1; ++r) memcpy((char *)dst + r * dpitch, (const char *)src + r * spitch, width);
+    });
+}
+
+static int ensure_bounce(gsn_ctx *ctx, size_t bytes) {
+    if (ctx->bounce_bytes >= bytes) return GSN_OK;
+    for (int b = 0; b < 4; ++b) {
+        if (ctx->bounce[b]) { cudaFreeHost(ctx->bounce[b]); ctx->bounce[b] = nullptr; }
+    }
+    ctx->bounce_bytes = 0;
+    for (int b = 0; b < 4; ++b) CU(cudaHostAlloc(&ctx->bounce[b], bytes, cudaHostAllocDefault));
+    ctx->bounce_bytes = bytes;
+    return GSN_OK;
+}
+
+// Pageable vector, multi-pass plan, blocks of at most 64 MB: the same column-block pipeline as enqueue_ntt768_host,
+// with the host threads gathering each input block into a pinned buffer (and scattering each output block from one)
+// while the DMA engines and the passes work on the neighbouring blocks.  *done stays false when the shape does not fit
+// (single pass, too few or too large blocks); the caller then uses the contiguous-chunk path below.
+static int ntt768_host_pageable_blocks(gsn_ctx *ctx, Plan768 *pl, uint32_t *limbs, size_t n, bool *done) {
+    *done = false;
+    int rc;
+    const size_t P = pl->digits.size();
+    if (P < 2) return GSN_OK;
+    const uint32_t l1 = pl->digits[0], lP = pl->digits[P - 1];
+    const uint64_t cols_in = n >> l1, rows_in = 1ull << l1, cols_out = 1ull << l1, rows_out = n >> l1;
+    const uint64_t tiles = n >> choose_log_tile768(ctx, pl, n);
+    int chunks = 8;
+    while (chunks > 1 && (cols_in % chunks || cols_out % chunks || tiles % chunks || (cols_in / chunks) * rows_in < 1024 ||
+                          (cols_out / chunks) * (1ull << lP) < 1024)) chunks >>= 1;
+    const size_t blk = n * 96 / chunks;
+    if (chunks < 4 || blk > ((size_t)64 << 20)) return GSN_OK;
+    if ((rc = ensure_io(ctx, n * 96)) || (rc = ensure_bounce(ctx, std::max(blk, (size_t)16 << 20)))) return rc;
+    cudaStream_t st = ctx->stream;
+    uint32_t *work_unused;
+    if ((rc = ensure_work(ctx, st, n * 96, &work_unused))) return rc;
+    uint32_t *io = (uint32_t *)ctx->io.p;
+    char *host = (char *)limbs;
+    CU(cudaEventRecord(ctx->ev0, st));   // the copy streams start after earlier work on the context
+    CU(cudaStreamWaitEvent(ctx->s_in, ctx->ev0, 0));
+    CU(cudaStreamWaitEvent(ctx->s_out, ctx->ev0, 0));
+    const uint64_t cw_in = cols_in / chunks, cw_out = cols_out / chunks, tiles_per_chunk = tiles / chunks;
+    for (int c = 0; c < chunks; ++c) {
+        const int b = c & 1;
+        if (c >= 2) CU(cudaEventSynchronize(ctx->ev_chunk[0][c - 2]));   // the DMA that last read this bounce buffer is done
+        copy_rows(ctx, ctx->bounce[b], cw_in * 96, host + c * cw_in * 96, cols_in * 96, cw_in * 96, rows_in);
+        CU(cudaMemcpy2DAsync(io + c * cw_in * 24, cols_in * 96, ctx->bounce[b], cw_in * 96, cw_in * 96, rows_in, cudaMemcpyHostToDevice, ctx->s_in));
+        CU(cudaEventRecord(ctx->ev_chunk[0][c], ctx->s_in));
+        CU(cudaStreamWaitEvent(st, ctx->ev_chunk[0][c], 0));
+        if ((rc = launch_ntt768_range(ctx, pl, io, 1, 0, ext_flat(nullptr), st, 0, 1, c * tiles_per_chunk, tiles_per_chunk))) return rc;
+    }
+    if (P > 2 && (rc = launch_ntt768_range(ctx, pl, io, 1, 0, ext_flat(nullptr), st, 1, P - 1, 0, 0))) return rc;
+    for (int c = 0; c < chunks; ++c) {
+        if ((rc = launch_ntt768_range(ctx, pl, io, 1, 0, ext_flat(nullptr), st, P - 1, P, c * tiles_per_chunk, tiles_per_chunk))) return rc;
+        CU(cudaEventRecord(ctx->ev_chunk[1][c], st));
+    }
+    auto copy_out = [&](int c) -> int {
+        CU(cudaStreamWaitEvent(ctx->s_out, ctx->ev_chunk[1][c], 0));
+        CU(cudaMemcpy2DAsync(ctx->bounce[2 + (c & 1)], cw_out * 96, io + c * cw_out * 24, cols_out * 96, cw_out * 96, rows_out, cudaMemcpyDeviceToHost, ctx->s_out));
+        CU(cudaEventRecord(ctx->ev_bounce[c & 1], ctx->s_out));
+        return GSN_OK;
+    };
+    for (int c = 0; c < std::min(2, chunks); ++c)
+        if ((rc = copy_out(c))) return rc;
+    for (int c = 0; c < chunks; ++c) {
+        CU(cudaEventSynchronize(ctx->ev_bounce[c & 1]));
+        copy_rows(ctx, host + c * cw_out * 96, cols_out * 96, ctx->bounce[2 + (c & 1)], cw_out * 96, cw_out * 96, rows_out);
+        if (c + 2 < chunks && (rc = copy_out(c + 2))) return rc;
+    }
+    CU(cudaStreamSynchronize(ctx->s_out));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaStreamSynchronize(ctx->s_in));
+    *done = true;
+    return GSN_OK;
 }
 
 static int ntt768_host_pageable(gsn_ctx *ctx, Plan768 *pl, uint32_t *limbs, size_t n) {
     int rc;
+    bool done = false;
+    if ((rc = ntt768_host_pageable_blocks(ctx, pl, limbs, n, &done)) || done) return rc;
     const size_t bytes = n * 96, chunk = (size_t)16 << 20;
-    if ((rc = ensure_io(ctx, bytes))) return rc;
-    if (ctx->bounce_bytes < chunk) {
-        for (int b = 0; b < 2; ++b) {
-            if (ctx->bounce[b]) cudaFreeHost(ctx->bounce[b]);
-            CU(cudaHostAlloc(&ctx->bounce[b], chunk, cudaHostAllocDefault));
-        }
-        ctx->bounce_bytes = chunk;
-    }
+    if ((rc = ensure_io(ctx, bytes)) || (rc = ensure_bounce(ctx, chunk))) return rc;
     char *dev = (char *)ctx->io.p, *host = (char *)limbs;
     cudaStream_t st = ctx->stream;
     size_t k = 0;
@@ -837,7 +975,7 @@ static int ntt768_host_pageable(gsn_ctx *ctx, Plan768 *pl, uint32_t *limbs, size
         const size_t len = std::min(chunk, bytes - off);
         const int b = (int)(k & 1);
         if (k >= 2) CU(cudaEventSynchronize(ctx->ev_chunk[0][b]));   // the DMA that last read this bounce buffer is done
-        parallel_memcpy(ctx->bounce[b], host + off, len);
+        copy_rows(ctx, ctx->bounce[b], len, host + off, len, len, 1);
         CU(cudaMemcpyAsync(dev + off, ctx->bounce[b], len, cudaMemcpyHostToDevice, st));
         CU(cudaEventRecord(ctx->ev_chunk[0][b], st));
     }
@@ -850,8 +988,9 @@ static int ntt768_host_pageable(gsn_ctx *ctx, Plan768 *pl, uint32_t *limbs, size
     }
     for (size_t c = 0; c < nchunks; ++c) {
         const int b = (int)(c & 1);
+        const size_t len = std::min(chunk, bytes - c * chunk);
         CU(cudaEventSynchronize(ctx->ev_chunk[1][b]));
-        parallel_memcpy(host + c * chunk, ctx->bounce[b], std::min(chunk, bytes - c * chunk));
+        copy_rows(ctx, host + c * chunk, len, ctx->bounce[b], len, len, 1);
         if (c + 2 < nchunks) {
             CU(cudaMemcpyAsync(ctx->bounce[b], dev + (c + 2) * chunk, std::min(chunk, bytes - (c + 2) * chunk), cudaMemcpyDeviceToHost, st));
             CU(cudaEventRecord(ctx->ev_chunk[1][b], st));

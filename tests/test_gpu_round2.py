@@ -242,6 +242,36 @@ def test_plan_cache_is_bounded(fresh):
     assert infos[-1]["cached_plans"] <= 3 and infos[-1]["cached_bytes"] <= 3 * (1 << 12) * 192 + 4096, infos
 
 
+@pytest.mark.parametrize("logn,threads", [(16, "1"), (18, "3"), (20, None), (21, "8")])
+def test_pageable_host_path_equals_device_path(logn, threads, monkeypatch):
+    """best_fft(std::vector&) hands the library pageable memory: gsn_ntt768_host then gathers column blocks into pinned
+    bounce buffers with a few host threads, pipelined with the DMA and the passes (2-pass plans at 2^16..2^20, a 3-pass
+    plan at 2^21).  Same bits as the device-resident call (itself oracle-checked), forward and inverse."""
+    import gpusnarks_b200 as g
+    if threads is None:
+        monkeypatch.delenv("GSN_HOST_THREADS", raising=False)
+    else:
+        monkeypatch.setenv("GSN_HOST_THREADS", threads)
+    ctx = g.Context(0)
+    try:
+        n = 1 << logn
+        w = fieldgen.omega768(n)
+        a = fieldgen.random_elements(n, 7100 + logn)       # a numpy array: pageable
+        d = ctx.device_alloc(a.nbytes)
+        for inverse in (False, True):
+            ctx.h2d(d, a)
+            ctx.ntt768_device(d, n, w, inverse=inverse)
+            want = np.empty_like(a)
+            ctx.d2h(want, d)
+            got = ctx.ntt768(a, w, inverse=inverse)
+            assert (got == want).all(), (logn, inverse)
+        if logn <= 16:
+            assert (want == _oracle(a, w, inverse=True)).all()
+        ctx.device_free(d)
+    finally:
+        ctx.close()
+
+
 @pytest.mark.parametrize("logn", [6, 12, 16, 21])
 def test_fourstep_plan_single_rank(fresh, logn):
     """gsn_fourstep with one rank: column transforms + (self) scatter + row transforms == the transform, both directions"""
