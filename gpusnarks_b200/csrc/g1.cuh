@@ -61,6 +61,12 @@ __device__ __forceinline__ bool fq_is_zero(const uint32_t *a) {
     for (int i = 0; i < NL; ++i) { all0 = all0 && a[i] == 0; allp = allp && a[i] == c_fq.p[i]; }
     return all0 || allp;
 }
+// exactly the Montgomery form of 1 (canonical): the Z of an affine input point
+__device__ __forceinline__ bool fq_is_one(const uint32_t *a) {
+    bool one = true;
+    for (int i = 0; i < NL; ++i) one = one && a[i] == c_fq.r1[i];
+    return one;
+}
 __device__ __forceinline__ void fq_copy(uint32_t *r, const uint32_t *a) {
     for (int i = 0; i < NL; ++i) r[i] = a[i];
 }
@@ -104,9 +110,15 @@ __device__ __noinline__ void g1_add(G1 &r, const G1 &p, const G1 &q) {
     if (fq_is_zero(p.z)) { g1_copy(r, q); return; }
     if (fq_is_zero(q.z)) { g1_copy(r, p); return; }
     uint32_t X1Z2[NL], Y1Z2[NL], Z1Z2[NL], u[NL], v[NL], uu[NL], vv[NL], vvv[NL], R[NL], A[NL], t[NL];
-    fq_mul(X1Z2, p.x, q.z);
-    fq_mul(Y1Z2, p.y, q.z);
-    fq_mul(Z1Z2, p.z, q.z);
+    if (fq_is_one(q.z)) {   // affine second operand (the usual input point): mixed addition, three products fewer
+        fq_copy(X1Z2, p.x);
+        fq_copy(Y1Z2, p.y);
+        fq_copy(Z1Z2, p.z);
+    } else {
+        fq_mul(X1Z2, p.x, q.z);
+        fq_mul(Y1Z2, p.y, q.z);
+        fq_mul(Z1Z2, p.z, q.z);
+    }
     fq_mul(u, q.y, p.z);
     fq_sub(u, u, Y1Z2);
     fq_mul(v, q.x, p.z);
@@ -275,20 +287,40 @@ __device__ __forceinline__ void g1_load_signed(G1 &P, const uint32_t *points, ui
     }
 }
 
-// one thread per (window, bucket): buckets[key] = sum of the (signed) points whose sorted key equals `key`.
-// A bucket with more than `limit` points would serialise one thread (scalars far below 2^768 leave the top windows with
-// a handful of digit values, each shared by a large fraction of the points): it is queued for g1_heavy_bucket_kernel.
+// Work list of the buckets one thread cannot take.  A bucket with more than `limit` points becomes one work item (one
+// block sums it); with more than G1_SPLIT_POINTS points it is cut into `parts` items whose partial sums land in `partial`
+// slots and are added by g1_heavy_combine_kernel.  (Scalars below 2^768 leave the top windows with a handful of digit
+// values -- the carry of the signed recoding alone puts about half of all points into ONE bucket of the last window.)
+struct G1HeavyItem { uint32_t key, part, parts, slot; };
+struct G1HeavySplit { uint32_t key, slot0, parts; };
+struct G1HeavyLists {
+    uint32_t *counters;      // [0] items, [1] partial slots, [2] split buckets
+    G1HeavyItem *items;
+    G1HeavySplit *splits;
+    uint32_t *partial;       // slots x 72 words
+};
+constexpr uint32_t G1_SPLIT_POINTS = 4096, G1_MAX_PARTS = 256;
+
+// one thread per (window, bucket): buckets[key] = sum of the (signed) points whose sorted key equals `key`
 __global__ void __launch_bounds__(128) g1_bucket_kernel(uint32_t *buckets, const uint32_t *points, const uint32_t *keys, const uint32_t *vals,
-                                                        uint64_t pairs, uint32_t nbuckets, uint32_t bs, uint32_t limit, uint32_t *heavy,
-                                                        uint32_t *heavy_count) {
+                                                        uint64_t pairs, uint32_t nbuckets, uint32_t bs, uint32_t limit, G1HeavyLists hl) {
     const uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
     if (key >= nbuckets) return;
     G1 acc, P, t;
     g1_set_identity(acc);
     if (key % bs != 0) {
         const uint64_t lo = g1_lower_bound(keys, pairs, key), hi = g1_lower_bound(keys, pairs, key + 1);
-        if (hi - lo > limit) {
-            heavy[atomicAdd(heavy_count, 1u)] = key;
+        const uint64_t size = hi - lo;
+        if (size > limit) {
+            uint32_t parts = 1;
+            if (size > G1_SPLIT_POINTS) parts = (uint32_t)min((uint64_t)G1_MAX_PARTS, (size + G1_SPLIT_POINTS - 1) / G1_SPLIT_POINTS);
+            const uint32_t j = atomicAdd(hl.counters, parts);
+            uint32_t slot0 = 0;
+            if (parts > 1) {
+                slot0 = atomicAdd(hl.counters + 1, parts);
+                hl.splits[atomicAdd(hl.counters + 2, 1u)] = G1HeavySplit{key, slot0, parts};
+            }
+            for (uint32_t k = 0; k < parts; ++k) hl.items[j + k] = G1HeavyItem{key, k, parts, slot0 + k};
         } else {
             for (uint64_t i = lo; i < hi; ++i) {
                 g1_load_signed(P, points, vals[i]);
@@ -300,39 +332,63 @@ __global__ void __launch_bounds__(128) g1_bucket_kernel(uint32_t *buckets, const
     g1_store(buckets + (uint64_t)key * 3 * NL, acc);
 }
 
-// one block per queued bucket: the threads stride over its points, then a shared-memory tree adds the partial sums
+// shared-memory tree over the THREADS partial sums of a block; the total ends in thread 0's `acc`
+template <int THREADS>
+__device__ __forceinline__ void g1_block_sum(G1 &acc, uint32_t *g1_red) {
+    G1 o, t;
+    uint32_t *mine = g1_red + threadIdx.x * 3 * NL;
+    for (int i = 0; i < NL; ++i) { mine[i] = acc.x[i]; mine[NL + i] = acc.y[i]; mine[2 * NL + i] = acc.z[i]; }
+    __syncthreads();
+    for (int half = THREADS / 2; half >= 1; half >>= 1) {
+        if ((int)threadIdx.x < half) {
+            const uint32_t *op = g1_red + (threadIdx.x + half) * 3 * NL;
+            for (int i = 0; i < NL; ++i) { acc.x[i] = mine[i]; acc.y[i] = mine[NL + i]; acc.z[i] = mine[2 * NL + i]; }
+            for (int i = 0; i < NL; ++i) { o.x[i] = op[i]; o.y[i] = op[NL + i]; o.z[i] = op[2 * NL + i]; }
+            g1_add(t, acc, o);
+            for (int i = 0; i < NL; ++i) { mine[i] = t.x[i]; mine[NL + i] = t.y[i]; mine[2 * NL + i] = t.z[i]; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        for (int i = 0; i < NL; ++i) { acc.x[i] = mine[i]; acc.y[i] = mine[NL + i]; acc.z[i] = mine[2 * NL + i]; }
+    __syncthreads();
+}
+
+// one block per work item: the threads stride over the item's share of the bucket, then a tree adds their partial sums
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) g1_heavy_bucket_kernel(uint32_t *buckets, const uint32_t *points, const uint32_t *keys, const uint32_t *vals,
-                                                                  uint64_t pairs, const uint32_t *heavy, const uint32_t *heavy_count) {
+                                                                  uint64_t pairs, G1HeavyLists hl) {
     extern __shared__ uint32_t g1_red[];  // THREADS * 72 words
-    for (uint32_t h = blockIdx.x; h < *heavy_count; h += gridDim.x) {
-        const uint32_t key = heavy[h];
-        const uint64_t lo = g1_lower_bound(keys, pairs, key), hi = g1_lower_bound(keys, pairs, key + 1);
+    const uint32_t count = hl.counters[0];
+    for (uint32_t h = blockIdx.x; h < count; h += gridDim.x) {
+        const G1HeavyItem it = hl.items[h];
+        const uint64_t lo = g1_lower_bound(keys, pairs, it.key), hi = g1_lower_bound(keys, pairs, it.key + 1), size = hi - lo;
+        const uint64_t a = lo + size * it.part / it.parts, b = lo + size * (it.part + 1) / it.parts;
         G1 acc, P, t;
         g1_set_identity(acc);
-        for (uint64_t i = lo + threadIdx.x; i < hi; i += THREADS) {
+        for (uint64_t i = a + threadIdx.x; i < b; i += THREADS) {
             g1_load_signed(P, points, vals[i]);
             g1_add(t, acc, P);
             g1_copy(acc, t);
         }
-        uint32_t *mine = g1_red + threadIdx.x * 3 * NL;
-        for (int i = 0; i < NL; ++i) { mine[i] = acc.x[i]; mine[NL + i] = acc.y[i]; mine[2 * NL + i] = acc.z[i]; }
-        __syncthreads();
-        for (int half = THREADS / 2; half >= 1; half >>= 1) {
-            if ((int)threadIdx.x < half) {
-                const uint32_t *o = g1_red + (threadIdx.x + half) * 3 * NL;
-                for (int i = 0; i < NL; ++i) { acc.x[i] = mine[i]; acc.y[i] = mine[NL + i]; acc.z[i] = mine[2 * NL + i]; }
-                for (int i = 0; i < NL; ++i) { P.x[i] = o[i]; P.y[i] = o[NL + i]; P.z[i] = o[2 * NL + i]; }
-                g1_add(t, acc, P);
-                for (int i = 0; i < NL; ++i) { mine[i] = t.x[i]; mine[NL + i] = t.y[i]; mine[2 * NL + i] = t.z[i]; }
-            }
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) {
-            for (int i = 0; i < NL; ++i) { acc.x[i] = mine[i]; acc.y[i] = mine[NL + i]; acc.z[i] = mine[2 * NL + i]; }
-            g1_store(buckets + (uint64_t)key * 3 * NL, acc);
-        }
-        __syncthreads();
+        g1_block_sum<THREADS>(acc, g1_red);
+        if (threadIdx.x == 0) g1_store(it.parts == 1 ? buckets + (uint64_t)it.key * 3 * NL : hl.partial + (uint64_t)it.slot * 3 * NL, acc);
+    }
+}
+
+// one block per split bucket: buckets[key] = sum of its `parts` partial sums
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) g1_heavy_combine_kernel(uint32_t *buckets, G1HeavyLists hl) {
+    static_assert(THREADS >= (int)G1_MAX_PARTS, "one partial per thread");
+    extern __shared__ uint32_t g1_red[];
+    const uint32_t count = hl.counters[2];
+    for (uint32_t h = blockIdx.x; h < count; h += gridDim.x) {
+        const G1HeavySplit sp = hl.splits[h];
+        G1 acc;
+        if (threadIdx.x < sp.parts) g1_load(acc, hl.partial + (uint64_t)(sp.slot0 + threadIdx.x) * 3 * NL);
+        else g1_set_identity(acc);
+        g1_block_sum<THREADS>(acc, g1_red);
+        if (threadIdx.x == 0) g1_store(buckets + (uint64_t)sp.key * 3 * NL, acc);
     }
 }
 

@@ -1171,32 +1171,38 @@ static int g1_multiexp_pippenger(gsn_ctx *ctx, uint32_t *d_out, const uint32_t *
     CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr, (uint32_t *)nullptr,
                                        (int)pairs, 0, key_bits, st));
     const uint32_t limit = 128;
-    const size_t heavy_cap = pairs / limit + 2;
+    // bounds of the heavy work list: every item but the split ones covers > limit points; a split bucket of s points has at most 2 s / 4096 parts
+    const size_t split_cap = pairs / gsn::G1_SPLIT_POINTS + 2, slot_cap = 2 * split_cap + gsn::G1_MAX_PARTS, item_cap = pairs / limit + slot_cap + 2;
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t o_keys = 0, o_vals = o_keys + up(pairs * 4), o_keys2 = o_vals + up(pairs * 4), o_vals2 = o_keys2 + up(pairs * 4),
-                 o_tmp = o_vals2 + up(pairs * 4), o_heavy = o_tmp + up(std::max<size_t>(tmp_bytes, 16)), o_buckets = o_heavy + up((heavy_cap + 1) * 4),
-                 o_wsum = o_buckets + up(nbuckets * 288), total_bytes = o_wsum + up((size_t)windows * 288);
+                 o_tmp = o_vals2 + up(pairs * 4), o_cnt = o_tmp + up(std::max<size_t>(tmp_bytes, 16)), o_items = o_cnt + 256,
+                 o_splits = o_items + up(item_cap * sizeof(gsn::G1HeavyItem)), o_partial = o_splits + up(split_cap * sizeof(gsn::G1HeavySplit)),
+                 o_buckets = o_partial + up(slot_cap * 288), o_wsum = o_buckets + up(nbuckets * 288), total_bytes = o_wsum + up((size_t)windows * 288);
     uint32_t *arena_w;
     if ((rc = ensure_work(ctx, st, total_bytes, &arena_w))) return rc;
     char *arena = (char *)arena_w;
     uint32_t *keys = (uint32_t *)(arena + o_keys), *vals = (uint32_t *)(arena + o_vals), *keys2 = (uint32_t *)(arena + o_keys2), *vals2 = (uint32_t *)(arena + o_vals2);
-    uint32_t *heavy_count = (uint32_t *)(arena + o_heavy), *heavy = heavy_count + 1, *buckets = (uint32_t *)(arena + o_buckets), *wsum = (uint32_t *)(arena + o_wsum);
-    CU(cudaMemsetAsync(heavy_count, 0, 4, st));
+    uint32_t *buckets = (uint32_t *)(arena + o_buckets), *wsum = (uint32_t *)(arena + o_wsum);
+    gsn::G1HeavyLists hl{(uint32_t *)(arena + o_cnt), (gsn::G1HeavyItem *)(arena + o_items), (gsn::G1HeavySplit *)(arena + o_splits),
+                         (uint32_t *)(arena + o_partial)};
+    CU(cudaMemsetAsync(hl.counters, 0, 16, st));
     gsn::g1_digits_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(keys, vals, d_scalars, n, c, windows, bs);
     CU(cub::DeviceRadixSort::SortPairs(arena + o_tmp, tmp_bytes, (const uint32_t *)keys, keys2, (const uint32_t *)vals, vals2, (int)pairs, 0, key_bits, st));
-    gsn::g1_bucket_kernel<<<(unsigned)((nbuckets + 127) / 128), 128, 0, st>>>(buckets, d_points, keys2, vals2, pairs, (uint32_t)nbuckets, bs, limit, heavy,
-                                                                              heavy_count);
+    gsn::g1_bucket_kernel<<<(unsigned)((nbuckets + 127) / 128), 128, 0, st>>>(buckets, d_points, keys2, vals2, pairs, (uint32_t)nbuckets, bs, limit, hl);
     constexpr int HT = 128, WT = 256;
     auto hv = gsn::g1_heavy_bucket_kernel<HT>;
+    auto cmb = gsn::g1_heavy_combine_kernel<WT>;
     auto red = gsn::g1_window_reduce_kernel<WT>;
     if (!ctx->smem_configured.count((const void *)red)) {
         CU(cudaFuncSetAttribute(red, cudaFuncAttributeMaxDynamicSharedMemorySize, WT * 288));
+        CU(cudaFuncSetAttribute(cmb, cudaFuncAttributeMaxDynamicSharedMemorySize, WT * 288));
         CU(cudaFuncSetAttribute(hv, cudaFuncAttributeMaxDynamicSharedMemorySize, HT * 288));
         ctx->smem_configured.insert((const void *)red);
     }
-    hv<<<(unsigned)std::min<size_t>(heavy_cap, (size_t)ctx->sm_count * 4), HT, HT * 288, st>>>(buckets, d_points, keys2, vals2, pairs, heavy, heavy_count);
+    hv<<<(unsigned)std::min<size_t>(item_cap, (size_t)ctx->sm_count * 4), HT, HT * 288, st>>>(buckets, d_points, keys2, vals2, pairs, hl);
+    cmb<<<(unsigned)std::min<size_t>(split_cap, (size_t)ctx->sm_count), WT, WT * 288, st>>>(buckets, hl);
     red<<<windows, WT, WT * 288, st>>>(wsum, buckets, c, bs);
-    ctx->launches += 4;
+    ctx->launches += 5;
     CU(cudaGetLastError());
     std::vector<gsn::host::G1Host> S(windows);
     static_assert(sizeof(gsn::host::G1Host) == 288, "three 96-byte coordinates");

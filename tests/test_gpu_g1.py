@@ -189,3 +189,28 @@ def test_heavy_buckets(fq_ctx):
     ks = [rng.randrange(1 << 20) for _ in range(n)]
     out = fq_ctx.g1_multiexp(_pack_points(pts), pyref.ints_to_array(ks), method="bucket")
     assert _affine(out) == g1ref.multiexp(base, [sum(ks[j::5]) for j in range(5)])
+
+
+def test_split_buckets(fq_ctx):
+    """buckets of more than 4096 points are cut into parts summed by several blocks and combined afterwards (the carry of
+    the signed recoding alone sends half of all points into one bucket of the last window): 10 000 and 9 000 points in
+    two buckets, projective (Z != 1) and affine inputs mixed, negative digits included"""
+    rng = random.Random(52)
+    base = [g1ref.random_point(rng) for _ in range(5)]
+    n = 19000
+    pts = [base[i % 5] for i in range(n)]
+    ks = [7 if i < 10000 else (9 << 8) for i in range(n)]        # window_bits 4: digit 7 of window 0; digit -7 of window 2 + carry
+    packed = _pack_points(pts)
+    out = fq_ctx.g1_multiexp(packed, pyref.ints_to_array(ks), method="bucket", window_bits=4)
+    want = g1ref.multiexp(base, [sum(ks[j::5]) for j in range(5)])
+    assert _affine(out) == want
+    # the same points in a non-affine projective representation (x l, y l, z l): the general addition path
+    p = pyref.FQ
+    lam = 0x1234567
+    scaled = packed.copy()
+    for i in range(5):
+        for c in range(3):
+            v = pyref.from_limbs(packed[i, c]) * lam % p
+            scaled[i::5, c] = np.array(pyref.to_limbs(v), dtype=np.uint32)
+    out = fq_ctx.g1_multiexp(scaled, pyref.ints_to_array(ks), method="bucket", window_bits=4)
+    assert _affine(out) == want
