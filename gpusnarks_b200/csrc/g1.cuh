@@ -404,20 +404,21 @@ __device__ __noinline__ void g1_mul_small(G1 &r, const G1 &p, uint32_t k) {
     g1_copy(r, acc);
 }
 
-// one block per window: S_w = sum_{b=1}^{nb} b * B[w][b], nb = 2^(c-1).  Thread t takes the buckets
-// (t m, (t+1) m], m = nb / THREADS: a descending running sum gives sum (b - t m) B_b and the chunk total T_t, the chunk
-// contributes that plus (t m) * T_t; the THREADS contributions are added by a shared-memory tree.  Canonical output.
+// gridDim.y blocks per window: S_w = sum_{b=1}^{nb} b * B[w][b], nb = 2^(c-1).  Block (w, j) takes the buckets
+// (j nb/P, (j+1) nb/P], thread t of it the m = nb / (P T) buckets above b0 = j nb/P + t m: a descending running sum gives
+// sum (b - b0) B_b and the chunk total T_t, the chunk contributes that plus b0 * T_t; the THREADS contributions are
+// added by a shared-memory tree.  out[w * P + j] (canonical); the host adds the P parts of a window.
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) g1_window_reduce_kernel(uint32_t *out, const uint32_t *buckets, uint32_t c, uint32_t bs) {
     extern __shared__ uint32_t g1_red[];  // THREADS * 72 words
-    const uint32_t w = blockIdx.x, nb = 1u << (c - 1);
+    const uint32_t w = blockIdx.x, nb = (1u << (c - 1)) / gridDim.y, base = blockIdx.y * nb;
     const uint32_t T = nb < (uint32_t)THREADS ? nb : (uint32_t)THREADS, m = nb / T;
     const uint32_t *B = buckets + (uint64_t)w * bs * 3 * NL;
     G1 run, sum, t, nxt;
     g1_set_identity(run);
     g1_set_identity(sum);
     if (threadIdx.x < T) {
-        const uint32_t b0 = threadIdx.x * m;
+        const uint32_t b0 = base + threadIdx.x * m;
         for (uint32_t b = b0 + m; b > b0; --b) {
             g1_load(nxt, B + (uint64_t)b * 3 * NL);
             g1_add(t, run, nxt);
@@ -431,25 +432,12 @@ __global__ void __launch_bounds__(THREADS) g1_window_reduce_kernel(uint32_t *out
             g1_copy(sum, t);
         }
     }
-    uint32_t *mine = g1_red + threadIdx.x * 3 * NL;
-    for (int i = 0; i < NL; ++i) { mine[i] = sum.x[i]; mine[NL + i] = sum.y[i]; mine[2 * NL + i] = sum.z[i]; }
-    __syncthreads();
-    for (int half = THREADS / 2; half >= 1; half >>= 1) {
-        if ((int)threadIdx.x < half) {
-            const uint32_t *o = g1_red + (threadIdx.x + half) * 3 * NL;
-            for (int i = 0; i < NL; ++i) { sum.x[i] = mine[i]; sum.y[i] = mine[NL + i]; sum.z[i] = mine[2 * NL + i]; }
-            for (int i = 0; i < NL; ++i) { nxt.x[i] = o[i]; nxt.y[i] = o[NL + i]; nxt.z[i] = o[2 * NL + i]; }
-            g1_add(t, sum, nxt);
-            for (int i = 0; i < NL; ++i) { mine[i] = t.x[i]; mine[NL + i] = t.y[i]; mine[2 * NL + i] = t.z[i]; }
-        }
-        __syncthreads();
-    }
+    g1_block_sum<THREADS>(sum, g1_red);
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NL; ++i) { sum.x[i] = mine[i]; sum.y[i] = mine[NL + i]; sum.z[i] = mine[2 * NL + i]; }
         canonicalize(c_fq, sum.x);
         canonicalize(c_fq, sum.y);
         canonicalize(c_fq, sum.z);
-        g1_store(out + (uint64_t)w * 3 * NL, sum);
+        g1_store(out + ((uint64_t)w * gridDim.y + blockIdx.y) * 3 * NL, sum);
     }
 }
 

@@ -962,6 +962,30 @@ static int ntt768_host_pageable_blocks(gsn_ctx *ctx, Plan768 *pl, uint32_t *limb
     return GSN_OK;
 }
 
+// host -> device copy of a possibly pageable buffer: a large pageable source goes through the pinned bounce buffers
+// (filled by the host threads while the DMA engine moves the previous chunk); returns with the copy complete
+static int h2d_staged(gsn_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t st) {
+    if (bytes < ((size_t)4 << 20) || !is_pageable(src)) {
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));
+        return GSN_OK;
+    }
+    int rc;
+    const size_t chunk = (size_t)16 << 20;
+    if ((rc = ensure_bounce(ctx, chunk))) return rc;
+    size_t k = 0;
+    for (size_t off = 0; off < bytes; off += chunk, ++k) {
+        const size_t len = std::min(chunk, bytes - off);
+        const int b = (int)(k & 1);
+        if (k >= 2) CU(cudaEventSynchronize(ctx->ev_chunk[0][b]));
+        copy_rows(ctx, ctx->bounce[b], len, (const char *)src + off, len, len, 1);
+        CU(cudaMemcpyAsync((char *)dst + off, ctx->bounce[b], len, cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(ctx->ev_chunk[0][b], st));
+    }
+    CU(cudaStreamSynchronize(st));
+    return GSN_OK;
+}
+
 static int ntt768_host_pageable(gsn_ctx *ctx, Plan768 *pl, uint32_t *limbs, size_t n) {
     int rc;
     bool done = false;
@@ -1171,13 +1195,14 @@ static int g1_multiexp_pippenger(gsn_ctx *ctx, uint32_t *d_out, const uint32_t *
     CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr, (uint32_t *)nullptr,
                                        (int)pairs, 0, key_bits, st));
     const uint32_t limit = 128;
+    const uint32_t wparts = nb >= 8192 ? 4 : nb >= 2048 ? 2 : 1;   // blocks per window of the running-sum reduction
     // bounds of the heavy work list: every item but the split ones covers > limit points; a split bucket of s points has at most 2 s / 4096 parts
     const size_t split_cap = pairs / gsn::G1_SPLIT_POINTS + 2, slot_cap = 2 * split_cap + gsn::G1_MAX_PARTS, item_cap = pairs / limit + slot_cap + 2;
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t o_keys = 0, o_vals = o_keys + up(pairs * 4), o_keys2 = o_vals + up(pairs * 4), o_vals2 = o_keys2 + up(pairs * 4),
                  o_tmp = o_vals2 + up(pairs * 4), o_cnt = o_tmp + up(std::max<size_t>(tmp_bytes, 16)), o_items = o_cnt + 256,
                  o_splits = o_items + up(item_cap * sizeof(gsn::G1HeavyItem)), o_partial = o_splits + up(split_cap * sizeof(gsn::G1HeavySplit)),
-                 o_buckets = o_partial + up(slot_cap * 288), o_wsum = o_buckets + up(nbuckets * 288), total_bytes = o_wsum + up((size_t)windows * 288);
+                 o_buckets = o_partial + up(slot_cap * 288), o_wsum = o_buckets + up(nbuckets * 288), total_bytes = o_wsum + up((size_t)windows * wparts * 288);
     uint32_t *arena_w;
     if ((rc = ensure_work(ctx, st, total_bytes, &arena_w))) return rc;
     char *arena = (char *)arena_w;
@@ -1201,12 +1226,12 @@ static int g1_multiexp_pippenger(gsn_ctx *ctx, uint32_t *d_out, const uint32_t *
     }
     hv<<<(unsigned)std::min<size_t>(item_cap, (size_t)ctx->sm_count * 4), HT, HT * 288, st>>>(buckets, d_points, keys2, vals2, pairs, hl);
     cmb<<<(unsigned)std::min<size_t>(split_cap, (size_t)ctx->sm_count), WT, WT * 288, st>>>(buckets, hl);
-    red<<<windows, WT, WT * 288, st>>>(wsum, buckets, c, bs);
+    red<<<dim3(windows, wparts), WT, WT * 288, st>>>(wsum, buckets, c, bs);
     ctx->launches += 5;
     CU(cudaGetLastError());
-    std::vector<gsn::host::G1Host> S(windows);
+    std::vector<gsn::host::G1Host> S((size_t)windows * wparts);
     static_assert(sizeof(gsn::host::G1Host) == 288, "three 96-byte coordinates");
-    CU(cudaMemcpyAsync(S.data(), wsum, (size_t)windows * 288, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(S.data(), wsum, (size_t)windows * wparts * 288, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     // Horner over the windows, most significant first: acc = 2^c acc + S_w
     gsn::host::G1Ops ops(gsn::host::fq_field());
@@ -1215,7 +1240,7 @@ static int g1_multiexp_pippenger(gsn_ctx *ctx, uint32_t *d_out, const uint32_t *
     for (uint32_t w = windows; w-- > 0;) {
         if (!ops.is_identity(acc))
             for (uint32_t k = 0; k < c; ++k) ops.dbl(acc, acc);
-        ops.add(acc, acc, S[w]);
+        for (uint32_t j = 0; j < wparts; ++j) ops.add(acc, acc, S[(size_t)w * wparts + j]);
     }
     CU(cudaMemcpyAsync(d_out, &acc, 288, cudaMemcpyHostToDevice, st));
     CU(cudaStreamSynchronize(st));
@@ -1276,8 +1301,7 @@ int gsn_g1_multiexp_host(gsn_ctx *ctx, uint32_t *out, const uint32_t *points, co
         std::lock_guard<std::mutex> lk(ctx->mu);
         CU(cudaSetDevice(ctx->device));
         if ((rc = dev_alloc(dp, std::max<size_t>(n, 1) * 288)) || (rc = dev_alloc(ds, std::max<size_t>(n, 1) * 96)) || (rc = dev_alloc(dout, 288))) return rc;
-        CU(cudaMemcpyAsync(dp.p, points, n * 288, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ds.p, scalars, n * 96, cudaMemcpyHostToDevice, ctx->stream));
+        if ((rc = h2d_staged(ctx, dp.p, points, n * 288, ctx->stream)) || (rc = h2d_staged(ctx, ds.p, scalars, n * 96, ctx->stream))) return rc;
     }
     if ((rc = gsn_g1_multiexp_device(ctx, (uint32_t *)dout.p, (const uint32_t *)dp.p, (const uint32_t *)ds.p, n, nullptr))) return rc;
     std::lock_guard<std::mutex> lk(ctx->mu);

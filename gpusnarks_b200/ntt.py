@@ -232,6 +232,11 @@ class Context:
                 self.device_free(p)
         return out
 
+    def g1_multiexp_device(self, d_out, d_points, d_scalars, n, method="auto", window_bits=0, stream=None):
+        """device-resident form (gsn_g1_multiexp_device_ex): 288-byte result at d_out"""
+        self._check(self.L.gsn_g1_multiexp_device_ex(self._h, C.c_void_p(d_out), C.c_void_p(d_points), C.c_void_p(d_scalars), int(n),
+                                                     {"auto": 0, "naive": 1, "bucket": 2}[method], int(window_bits), C.c_void_p(stream or 0)))
+
     def coset_ntt768(self, a, omega, shift, inverse=False):
         """forward: evaluations of the polynomial with coefficients a on the coset shift * <omega>;
         inverse: coefficients from such evaluations.  Host arrays in/out (gsn_coset_ntt768_host)."""

@@ -76,6 +76,16 @@ def main():
     out = ctx.g1_multiexp(P, pyref.ints_to_array(ks), method="bucket", window_bits=4)
     aff = g1ref.from_projective_mont(*[pyref.from_limbs(out[c]) for c in range(3)])
     assert aff == g1ref.multiexp(pts, [sum(ks[j::8]) for j in range(8)])
+    # split buckets: 9 000 points in one bucket (three parts + the combine kernel), and the split window reduction (c = 13)
+    P2 = P[np.arange(9000) % 8]
+    out = ctx.g1_multiexp(P2, pyref.ints_to_array([7] * 9000), method="bucket", window_bits=13)
+    aff = g1ref.from_projective_mont(*[pyref.from_limbs(out[c]) for c in range(3)])
+    assert aff == g1ref.multiexp(pts, [7 * 1125] * 8)
+    # pageable host path: column blocks through the pinned bounce buffers (numpy memory is pageable), 2^16 = two passes
+    n = 1 << 16
+    a = fieldgen.random_elements(n, 9200)
+    w = fieldgen.omega768(n)
+    assert (ctx.ntt768(ctx.ntt768(a, w), w, inverse=True) == a).all()
     q = g1ref.Q
     fa = np.stack([fieldgen.random_elements(64, 1, q), fieldgen.random_elements(64, 2, q)], axis=1)
     ctx.fp2_binop("mul", fa, fa)
