@@ -183,6 +183,45 @@ def executed_utilisation(logn, ms_step, p_mac):
             "frac_of_peak": slots / (ms_step * 1e-3) / p_mac}
 
 
+def bench_g1(ctx, logn=16, reps=3):
+    """MNT4-753 G1 multi-exponentiation, the reference README's shape (2^16 points, full-width
+    scalars), device resident.  Curve points come from tests/g1ref.py (input generation only; parity is tests/test_gpu_g1.py)."""
+    import random
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import g1ref
+    import pyref
+    n = 1 << logn
+    rng = random.Random(7)
+    packed = np.zeros((64, 3, 24), dtype=np.uint32)
+    for i in range(64):
+        for c, v in enumerate(g1ref.to_projective_mont(g1ref.random_point(rng))):
+            packed[i, c] = pyref.to_limbs(v)
+    pts = packed[np.arange(n) % 64]
+    ks = np.random.Generator(np.random.PCG64(logn)).integers(0, 1 << 32, size=(n, 24), dtype=np.uint64).astype(np.uint32)
+    ks[:, 23] &= 0xFFFF   # < 2^752
+    dp, ds, do = ctx.device_alloc(n * 288), ctx.device_alloc(n * 96), ctx.device_alloc(288)
+    try:
+        ctx.h2d(dp, pts)
+        ctx.h2d(ds, ks)
+        out = {}
+        for method, r in (("bucket", reps + 1), ("naive", 1)):
+            ms = []
+            for _ in range(r):
+                ctx.synchronize()
+                t0 = time.perf_counter()
+                ctx.g1_multiexp_device(do, dp, ds, n, method=method)
+                ctx.synchronize()
+                ms.append((time.perf_counter() - t0) * 1e3)
+            out[method] = min(ms[1:]) if len(ms) > 1 else ms[0]
+    finally:
+        for p in (dp, ds, do):
+            ctx.device_free(p)
+    return {"workload": f"MNT4-753 G1 multi-exponentiation, 2^{logn} points (64 distinct, affine), 752-bit scalars, device resident, 1xB200",
+            "ms": out["bucket"], "points_per_s": n / (out["bucket"] * 1e-3), "algorithm": "bucket method (gsn_g1_multiexp_device_ex, automatic window)",
+            "reference_algorithm_ms": out["naive"],
+            "reference_algorithm": "one double-and-add per point + tree reduction (cuda/multi_exp.cu:86-137) on the same field arithmetic"}
+
+
 def bench_ntt32(ctx, hbm_peak_gbs, logn=22, batch=16, reps=12):
     """BASELINE.json configs[1]: 32-bit prime-field NTT 2^22 on one B200 (HBM-bound).  `batch` distinct
     16 MiB buffers (256 MiB > L2) are transformed per launch pair so that inputs come from HBM; the
@@ -454,6 +493,10 @@ def run_single(args, torch, g, F, ctx, dev, stream, logn, config, rates):
         secondary["ntt32_cfg2"] = bench_ntt32(ctx, peaks_file().get("hbm_gbs", 6650.0))
     except Exception as e:
         secondary["ntt32_cfg2"] = {"error": str(e)}
+    try:
+        secondary["g1_multiexp_2pow16"] = bench_g1(ctx)
+    except Exception as e:
+        secondary["g1_multiexp_2pow16"] = {"error": str(e)}
     line["secondary"] = secondary
     unbind_cpus()
     try:
