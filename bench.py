@@ -171,13 +171,13 @@ def ncu_traffic_bytes(name, per="launch", divide=1.0):
 
 def executed_utilisation(logn, ms_step, p_mac):
     """wide-multiply issue slots the single-GPU transform really executes (fixed-operand product: 876 IMAD.WIDE + 48 IMAD
-    = 900 wide-equivalents; per pass of l stages a tile runs l - 1.875 stages' worth of products -- stage 1 and the unit
-    butterflies of stages 2-4 are skipped -- plus one product per element at every pass boundary) / time / peak"""
+    = 900 wide-equivalents; per pass of l stages a tile runs l - 1.9375 stages' worth of products -- stage 1 and the unit
+    butterflies of stages 2-5 are skipped -- plus one product per element at every pass boundary) / time / peak"""
     n = 1 << logn
     passes = max(1, -(-logn // 10))
     base, extra = divmod(logn, passes)
     digits = [base + (1 if i < extra else 0) for i in range(passes)]
-    products = sum((max(l - 1.875, 0)) * n / 2 for l in digits) + (passes - 1) * n
+    products = sum((max(l - 1.9375, 0)) * n / 2 for l in digits) + (passes - 1) * n
     slots = products * 900.0
     return {"products_per_transform": products, "wide_equiv_slots_per_product": 900, "slots_per_s": slots / (ms_step * 1e-3),
             "frac_of_peak": slots / (ms_step * 1e-3) / p_mac}
