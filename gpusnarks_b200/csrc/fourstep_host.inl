@@ -501,7 +501,89 @@ int gsn_multi_create(gsn_multi **out, const int *devices, unsigned n_devices, si
     return GSN_OK;
 }
 
-// natural-order host vector -> column layouts (forward) / row layouts -> natural order, by strided 2-D copies
+}  // extern "C"
+
+// One rank's buffer as rows of runs inside the natural-order host vector:
+//   column layout (rank g)  x_g[i1][c], c = (c_hi, c_lo): a[i1 n2 + (c_hi, g, c_lo)]   n1 rows of C/2^cl runs of 2^cl elements
+//   row layout (rank h)     y_h[k2][r] = A[(h R + r) + n1 k2]                          n2 rows of one run of R elements
+struct MultiLayout {
+    uint64_t rows, row_bytes;        // the device buffer: rows x row_bytes, contiguous
+    uint64_t run_bytes, runs;        // a row is `runs` runs of run_bytes
+    uint64_t row_stride, run_stride; // bytes between rows / runs in the host vector
+    uint64_t rank_offset;            // bytes: host position of rank g's first run = g * rank_offset
+};
+
+// Pageable host vector <-> the ranks' device buffers through the pinned bounce buffers of context 0: host threads
+// gather (scatter) 16 MB pieces while the DMA engines of up to four devices move the previous ones.
+static int multi_staged_copy(gsn_multi *m, bool to_device, const MultiLayout &L, char *host, const std::vector<char *> &dev) {
+    gsn_ctx *c0 = m->ctxs[0];
+    int rc;
+    const uint64_t piece_rows = std::max<uint64_t>(1, std::min<uint64_t>(L.rows, ((uint64_t)16 << 20) / L.row_bytes));
+    if ((rc = ensure_bounce(c0, std::max<size_t>(piece_rows * L.row_bytes, (size_t)16 << 20)))) return rc;
+    const uint64_t pieces = (L.rows + piece_rows - 1) / piece_rows, items = pieces * m->G;
+    auto rows_of = [&](uint64_t item, uint64_t &r0, uint64_t &nr, unsigned &g) {
+        g = (unsigned)(item % m->G);
+        r0 = (item / m->G) * piece_rows;
+        nr = std::min(piece_rows, L.rows - r0);
+    };
+    auto host_side = [&](uint64_t item, bool gather) {
+        uint64_t r0, nr;
+        unsigned g;
+        rows_of(item, r0, nr, g);
+        char *bounce = (char *)c0->bounce[item & 3];
+        char *base = host + g * L.rank_offset;
+        const MultiLayout l = L;
+        host_pool(c0).run([=](unsigned t, unsigned nt) {
+            for (uint64_t r = nr * t / nt; r < nr * (t + 1) / nt; ++r)
+                for (uint64_t k = 0; k < l.runs; ++k) {
+                    char *h = base + (r0 + r) * l.row_stride + k * l.run_stride, *b = bounce + r * l.row_bytes + k * l.run_bytes;
+                    if (gather) memcpy(b, h, l.run_bytes);
+                    else memcpy(h, b, l.run_bytes);
+                }
+        });
+    };
+    auto dma = [&](uint64_t item) -> int {
+        uint64_t r0, nr;
+        unsigned g;
+        rows_of(item, r0, nr, g);
+        gsn_ctx *c = m->ctxs[g];
+        CU(cudaSetDevice(c->device));
+        char *d = dev[g] + r0 * L.row_bytes, *b = (char *)c0->bounce[item & 3];
+        if (to_device) CU(cudaMemcpyAsync(d, b, nr * L.row_bytes, cudaMemcpyHostToDevice, c->stream));
+        else CU(cudaMemcpyAsync(b, d, nr * L.row_bytes, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaEventRecord(c->ev_chunk[0][item & 3], c->stream));
+        return GSN_OK;
+    };
+    auto wait = [&](uint64_t item) -> int {   // the DMA of `item` (on its device's stream) has finished
+        gsn_ctx *c = m->ctxs[item % m->G];
+        CU(cudaSetDevice(c->device));
+        CU(cudaEventSynchronize(c->ev_chunk[0][item & 3]));
+        return GSN_OK;
+    };
+    if (to_device) {
+        for (uint64_t it = 0; it < items; ++it) {
+            if (it >= 4 && (rc = wait(it - 4))) return rc;
+            host_side(it, true);
+            if ((rc = dma(it))) return rc;
+        }
+        for (uint64_t it = items > 4 ? items - 4 : 0; it < items; ++it)
+            if ((rc = wait(it))) return rc;     // the bounce buffers are free again when this returns
+    } else {
+        for (uint64_t it = 0; it < std::min<uint64_t>(4, items); ++it)
+            if ((rc = dma(it))) return rc;
+        for (uint64_t it = 0; it < items; ++it) {
+            if ((rc = wait(it))) return rc;
+            host_side(it, false);
+            if (it + 4 < items && (rc = dma(it + 4))) return rc;
+        }
+    }
+    return GSN_OK;
+}
+
+extern "C" {
+
+// natural-order host vector -> column layouts (forward) / row layouts -> natural order: strided 2-D copies straight from
+// pinned memory, pieces staged through pinned bounce buffers by host threads when the vector is pageable (a std::vector)
 int gsn_multi_ntt768_host(gsn_multi *m, uint32_t *limbs, int inverse) {
     if (!m || !limbs) return fail(GSN_ERR_INVALID_ARG, "null argument");
     const unsigned G = m->G;
@@ -509,6 +591,30 @@ int gsn_multi_ntt768_host(gsn_multi *m, uint32_t *limbs, int inverse) {
     const uint64_t n1 = 1ull << f0->log_n1, n2 = 1ull << f0->log_n2, C = n2 / G, R = n1 / G;
     const uint64_t runw = 1ull << f0->cl;                 // columns of one rank come in runs of 2^cl, every G * 2^cl
     int rc;
+    const bool staged = ((uint64_t)96 << m->logn) >= ((uint64_t)4 << 20) && is_pageable(limbs);
+    const MultiLayout col{n1, C * 96, runw * 96, C >> f0->cl, n2 * 96, G * runw * 96, runw * 96};
+    const MultiLayout row{n2, R * 96, R * 96, 1, n1 * 96, 0, R * 96};
+    std::vector<char *> xs(G), ys(G);
+    auto buffers = [&] {
+        for (unsigned g = 0; g < G; ++g) { xs[g] = (char *)m->plans[g]->x.p; ys[g] = (char *)m->plans[g]->y[m->plans[g]->flip].p; }
+    };
+    auto sync_all = [&]() -> int {
+        for (unsigned g = 0; g < G; ++g) {
+            CU(cudaSetDevice(m->ctxs[g]->device));
+            CU(cudaStreamSynchronize(m->ctxs[g]->stream));
+        }
+        return GSN_OK;
+    };
+    if (staged) {
+        buffers();
+        if ((rc = multi_staged_copy(m, true, inverse ? row : col, (char *)limbs, inverse ? ys : xs))) return rc;
+        for (unsigned g = 0; g < G; ++g)
+            if ((rc = inverse ? gsn_fourstep_inverse(m->plans[g], nullptr, nullptr) : gsn_fourstep_forward(m->plans[g], nullptr, nullptr))) return rc;
+        if ((rc = sync_all())) return rc;
+        buffers();   // forward flips the y buffers
+        if ((rc = multi_staged_copy(m, false, inverse ? col : row, (char *)limbs, inverse ? xs : ys))) return rc;
+        return sync_all();
+    }
     if (!inverse) {
         // rank g, local column c = (c_hi, c_lo): a[i1 * n2 + (c_hi, g, c_lo)]  ->  x_g[i1][c]
         for (unsigned g = 0; g < G; ++g) {
@@ -543,11 +649,7 @@ int gsn_multi_ntt768_host(gsn_multi *m, uint32_t *limbs, int inverse) {
                                      cudaMemcpyDeviceToHost, c->stream));
         }
     }
-    for (unsigned g = 0; g < G; ++g) {
-        cudaSetDevice(m->ctxs[g]->device);
-        CU(cudaStreamSynchronize(m->ctxs[g]->stream));
-    }
-    return GSN_OK;
+    return sync_all();
 }
 
 int gsn_multi_device_buffers(gsn_multi *m, unsigned rank, void **x, void **y) {

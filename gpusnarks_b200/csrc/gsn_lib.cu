@@ -620,6 +620,13 @@ int check_n(size_t n, size_t batch) {
 
 }  // namespace
 
+// host-side staging helpers of the pageable paths (defined with the host-pointer entry points below)
+extern "C" {
+static bool is_pageable(const void *p);
+static HostPool &host_pool(gsn_ctx *ctx);
+static int ensure_bounce(gsn_ctx *ctx, size_t bytes);
+}
+
 #include "ntt32_host.inl"
 #include "fourstep_host.inl"
 
@@ -896,7 +903,7 @@ static int ensure_bounce(gsn_ctx *ctx, size_t bytes) {
         if (ctx->bounce[b]) { cudaFreeHost(ctx->bounce[b]); ctx->bounce[b] = nullptr; }
     }
     ctx->bounce_bytes = 0;
-    for (int b = 0; b < 4; ++b) CU(cudaHostAlloc(&ctx->bounce[b], bytes, cudaHostAllocDefault));
+    for (int b = 0; b < 4; ++b) CU(cudaHostAlloc(&ctx->bounce[b], bytes, cudaHostAllocPortable));   // the multi-GPU host entry DMAs from them on every device
     ctx->bounce_bytes = bytes;
     return GSN_OK;
 }

@@ -304,9 +304,12 @@ def test_fourstep_plan_single_rank(fresh, logn):
         plan.close()
 
 
-@pytest.mark.parametrize("logn", [14, 21])
-def test_multi_gpu_entry_point_one_process(logn):
-    """gsn_multi_*: every visible device (1, 2, 4 or 8) driven from this one process; host vector in natural order"""
+@pytest.mark.parametrize("logn,pinned", [(14, False), (21, False), (21, True)])
+def test_multi_gpu_entry_point_one_process(logn, pinned):
+    """gsn_multi_*: every visible device (1, 2, 4 or 8) driven from this one process; host vector in natural order.
+    A pageable vector (numpy / std::vector) of 4 MiB and more is staged through pinned bounce buffers by host threads,
+    a pinned one is copied by strided 2-D DMAs directly: both forms are checked."""
+    import torch
     import gpusnarks_b200 as g
     from gpusnarks_b200.ntt import MultiGpu
     cnt = g.device_count()
@@ -318,7 +321,11 @@ def test_multi_gpu_entry_point_one_process(logn):
     w = fieldgen.omega768(n)
     m = MultiGpu(list(range(G)), n, w)
     try:
-        v = a.copy()
+        if pinned:
+            keep = torch.from_numpy(a.view(np.int32)).clone().pin_memory()
+            v = keep.numpy().view(np.uint32)
+        else:
+            v = a.copy()
         m.ntt_host(v)
         c = g.Context(0)
         try:
