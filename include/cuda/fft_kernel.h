@@ -83,6 +83,8 @@ template <typename FieldT> struct fft_dispatch;  // no generic definition: unkno
 template <> struct fft_dispatch<fields::Scalar> {
     static void run(std::vector<fields::Scalar> &a, const fields::Scalar &omg, int inverse) {
         if (gsn_multi *m = default_multi(a.size(), omg.im_rep)) {
+            static std::mutex call_mu;   // a gsn_multi owns its devices for the duration of a call: one sharded transform at a time
+            std::lock_guard<std::mutex> lk(call_mu);
             check(gsn_multi_ntt768_host(m, reinterpret_cast<uint32_t *>(a.data()), inverse), "gsn_multi_ntt768_host");
             return;
         }
