@@ -80,7 +80,10 @@ int gsn_launch_count(gsn_ctx *ctx, uint64_t *count);
 
 /* ---- 768-bit NTT.  Replaces best_fft<fields::Scalar> (reference cuda/fft_kernel.cu:117-150).
  * host variant: `limbs` is host memory (n * 24 words), copied H2D, transformed, copied back
- * (blocking, like the reference's two cudaMemcpy, fft_kernel.cu:131,144). */
+ * (blocking, like the reference's two cudaMemcpy, fft_kernel.cu:131,144).  Pinned or pageable: multi-pass sizes are
+ * pipelined in column blocks (copy-in, first pass, last pass and copy-out of neighbouring blocks overlap); a pageable
+ * vector (std::vector) of 4 MiB or more is staged through pinned bounce buffers by a few host threads inside the
+ * call (environment GSN_HOST_THREADS, default min(8, cores / 2)). */
 int gsn_ntt768_host(gsn_ctx *ctx, uint32_t *limbs, size_t n, const uint32_t omega[GSN_FP768_LIMBS], int inverse);
 /* `count` independent host vectors of n elements each, transformed in place.  Same result as `count`
  * calls of gsn_ntt768_host, but the copy-in of vector i+1 overlaps the passes and the copy-out of vector i
