@@ -26,6 +26,7 @@
 #include "../../include/gpusnarks_b200.h"
 #include "../../include/gsn_constants.h"
 #include "fp768.cuh"
+#include "host_pool.h"
 #include "g1.cuh"
 #include "../../include/fields/g1_host.h"
 #include "../../include/fields/fp768_host.h"
@@ -124,61 +125,6 @@ struct StreamWork {   // scratch buffer of the multi-pass transforms, one per st
 }  // namespace
 
 struct gsn_coset_entry;
-
-// A few persistent host threads that move data between a caller's pageable memory and the pinned bounce buffers
-// (run() blocks; the calling thread works as thread 0).
-struct HostPool {
-    std::vector<std::thread> threads;
-    std::mutex m;
-    std::condition_variable cv, done_cv;
-    const std::function<void(unsigned, unsigned)> *job = nullptr;
-    uint64_t epoch = 0;
-    unsigned pending = 0, nt = 1;
-    bool stop = false;
-    explicit HostPool(unsigned n) : nt(std::max(1u, n)) {
-        for (unsigned t = 1; t < nt; ++t)
-            threads.emplace_back([this, t] {
-                uint64_t seen = 0;
-                for (;;) {
-                    const std::function<void(unsigned, unsigned)> *fn;
-                    {
-                        std::unique_lock<std::mutex> lk(m);
-                        cv.wait(lk, [&] { return stop || epoch != seen; });
-                        if (stop) return;
-                        seen = epoch;
-                        fn = job;
-                    }
-                    (*fn)(t, nt);
-                    {
-                        std::lock_guard<std::mutex> lk(m);
-                        if (--pending == 0) done_cv.notify_one();
-                    }
-                }
-            });
-    }
-    ~HostPool() {
-        {
-            std::lock_guard<std::mutex> lk(m);
-            stop = true;
-        }
-        cv.notify_all();
-        for (auto &t : threads) t.join();
-    }
-    void run(const std::function<void(unsigned, unsigned)> &fn) {
-        if (nt > 1) {
-            std::lock_guard<std::mutex> lk(m);
-            job = &fn;
-            pending = nt - 1;
-            ++epoch;
-        }
-        cv.notify_all();
-        fn(0, nt);
-        if (nt > 1) {
-            std::unique_lock<std::mutex> lk(m);
-            done_cv.wait(lk, [&] { return pending == 0; });
-        }
-    }
-};
 
 struct gsn_ctx {
     int device = 0;

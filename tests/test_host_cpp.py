@@ -163,6 +163,16 @@ def test_large_tile_kernel_index_model(tmp_path):
     assert out.returncode == 0 and "test_v2_index: ok" in out.stdout, out.stdout + out.stderr
 
 
+def test_host_copy_pool(tmp_path):
+    """the persistent host thread pool of the pageable paths (csrc/host_pool.h): every thread index runs exactly once per
+    run(), run() is a barrier, back-to-back runs neither lose nor repeat work, a pitched copy split over it is exact"""
+    exe = str(tmp_path / "test_host_pool")
+    subprocess.check_call([CXX, "-O2", "-std=c++17", "-Wall", "-pthread", "-I" + os.path.join(ROOT, "gpusnarks_b200", "csrc"), "-o", exe,
+                           os.path.join(ROOT, "tests", "cpp", "test_host_pool.cpp")])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "test_host_pool: ok" in out.stdout, out.stdout + out.stderr
+
+
 def test_fused_layout_helpers():
     """column / row layouts of the fused four-step plan (block-cyclic column ownership, [k2][r] rows) are bijections
     and agree with the definitions in include/gpusnarks_b200.h"""
