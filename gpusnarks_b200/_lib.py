@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("GSN_LIB") or os.path.join(HERE, "libgpusnarks_b200.so
 SYMBOLS = [
     "gsn_ctx_create", "gsn_ctx_destroy", "gsn_last_error", "gsn_set_field768", "gsn_ctx_trim", "gsn_launch_count",
     "gsn_ntt768_host", "gsn_ntt768_host_batch", "gsn_ntt768_device", "gsn_ntt768_prepare", "gsn_ntt768_strided_device",
-    "gsn_ntt768_device_ex", "gsn_fourstep_table768", "gsn_ntt768_device_scatter", "gsn_peer_barrier", "gsn_ipc_export", "gsn_ipc_import", "gsn_ipc_close", "gsn_fp768_binop_host", "gsn_fp768_binop_device", "gsn_fp768_powers_device", "gsn_fp768_twiddle_table_device", "gsn_fp768_inner_product_device", "gsn_fp768_inner_product_host", "gsn_g1_multiexp_host", "gsn_g1_multiexp_device", "gsn_g1_multiexp_device_ex", "gsn_fp2_binop_host", "gsn_fp2_binop_device", "gsn_ntt32_host", "gsn_ntt32_device",
+    "gsn_ntt768_device_ex", "gsn_fourstep_table768", "gsn_ntt768_device_scatter", "gsn_peer_barrier", "gsn_ipc_export", "gsn_ipc_import", "gsn_ipc_close", "gsn_fp768_binop_host", "gsn_fp768_binop_device", "gsn_fp768_powers_device", "gsn_fp768_twiddle_table_device", "gsn_fp768_inner_product_device", "gsn_fp768_inner_product_host", "gsn_g1_multiexp_host", "gsn_g1_multiexp_multi_host", "gsn_g1_multiexp_device", "gsn_g1_multiexp_device_ex", "gsn_fp2_binop_host", "gsn_fp2_binop_device", "gsn_ntt32_host", "gsn_ntt32_device",
     "gsn_device_count", "gsn_host_alloc", "gsn_host_free", "gsn_device_alloc", "gsn_device_free",
     "gsn_memcpy_h2d", "gsn_memcpy_d2h", "gsn_ctx_synchronize", "gsn_int32_issue_rates",
     "gsn_ntt768_time_device", "gsn_ntt32_time_device",
@@ -65,6 +65,7 @@ def load():
     L.gsn_fp768_inner_product_device.argtypes = [vp, vp, vp, vp, sz, vp]
     L.gsn_fp768_inner_product_host.argtypes = [vp, u32p, u32p, u32p, sz]
     L.gsn_g1_multiexp_host.argtypes = [vp, u32p, u32p, u32p, sz]
+    L.gsn_g1_multiexp_multi_host.argtypes = [C.POINTER(C.c_int), C.c_uint, u32p, u32p, u32p, sz]
     L.gsn_g1_multiexp_device.argtypes = [vp, vp, vp, vp, sz, vp]
     L.gsn_fp2_binop_host.argtypes = [vp, i, u32p, u32p, u32p, sz]
     L.gsn_fp2_binop_device.argtypes = [vp, i, vp, vp, vp, sz, vp]

@@ -1263,6 +1263,57 @@ int gsn_g1_multiexp_host(gsn_ctx *ctx, uint32_t *out, const uint32_t *points, co
     return GSN_OK;
 }
 
+int gsn_g1_multiexp_multi_host(const int *devices, unsigned n_devices, uint32_t *out, const uint32_t *points, const uint32_t *scalars, size_t n) {
+    if (!out || (n && (!points || !scalars))) return fail(GSN_ERR_INVALID_ARG, "null argument");
+    int visible = 0;
+    CU(cudaGetDeviceCount(&visible));
+    std::vector<int> devs;
+    if (n_devices == 0) for (int d = 0; d < visible; ++d) devs.push_back(d);
+    else {
+        if (!devices) return fail(GSN_ERR_INVALID_ARG, "null device list");
+        devs.assign(devices, devices + n_devices);
+    }
+    for (int d : devs) if (d < 0 || d >= visible) return fail(GSN_ERR_INVALID_ARG, "device %d of %d", d, visible);
+    if (devs.empty()) return fail(GSN_ERR_INVALID_ARG, "no device");
+    // one context per device, created on first use and kept for the life of the process
+    static std::mutex mu;
+    static std::vector<gsn_ctx *> cached;
+    std::vector<gsn_ctx *> ctxs;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if ((int)cached.size() < visible) cached.resize(visible, nullptr);
+        for (int d : devs) {
+            if (!cached[d]) {
+                int rc = gsn_ctx_create(&cached[d], d);
+                if (rc) return rc;
+            }
+            ctxs.push_back(cached[d]);
+        }
+    }
+    const size_t G = devs.size(), per = (n + G - 1) / G;
+    std::vector<gsn::host::G1Host> part(G);
+    std::vector<int> rcs(G, GSN_OK);
+    std::vector<std::string> errs(G);
+    std::vector<std::thread> threads;
+    for (size_t g = 0; g < G; ++g) {
+        const size_t lo = std::min(n, g * per), cnt = std::min(n, lo + per) - lo;
+        threads.emplace_back([&, g, lo, cnt] {
+            if (cnt == 0) { gsn::host::G1Ops(gsn::host::fq_field()).identity(part[g]); return; }   // an empty slice
+            rcs[g] = gsn_g1_multiexp_host(ctxs[g], (uint32_t *)&part[g], points + lo * 72, scalars + lo * 24, cnt);
+            if (rcs[g]) errs[g] = gsn_last_error();   // the message is thread local
+        });
+    }
+    for (auto &t : threads) t.join();
+    for (size_t g = 0; g < G; ++g)
+        if (rcs[g]) return fail(rcs[g], "device %d: %s", devs[g], errs[g].c_str());
+    gsn::host::G1Ops ops(gsn::host::fq_field());
+    gsn::host::G1Host acc;
+    ops.identity(acc);
+    for (size_t g = 0; g < G; ++g) ops.add(acc, acc, part[g]);
+    memcpy(out, &acc, 288);
+    return GSN_OK;
+}
+
 int gsn_fp768_binop_host(gsn_ctx *ctx, int op, uint32_t *out, const uint32_t *a, const uint32_t *b, size_t count) {
     if (!ctx || !out || !a || !b) return fail(GSN_ERR_INVALID_ARG, "null argument");
     if (op < 0 || op > 2) return fail(GSN_ERR_INVALID_ARG, "op %d", op);

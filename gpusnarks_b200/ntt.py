@@ -382,6 +382,22 @@ class MultiGpu:
             self._h = None
 
 
+def g1_multiexp_multi(points, scalars, devices=None):
+    """gsn_g1_multiexp_multi_host: sum_i scalars[i] * points[i] with the points cut into one slice per device
+    (devices=None: every visible device); returns the (3, 24) projective result"""
+    L = _lib.load()
+    points = np.ascontiguousarray(points, dtype=np.uint32).reshape(-1, 3, NL)
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint32).reshape(-1, NL)
+    assert points.shape[0] == scalars.shape[0]
+    out = np.empty((3, NL), dtype=np.uint32)
+    devs = list(devices) if devices is not None else []
+    arr = (C.c_int * max(len(devs), 1))(*devs)
+    rc = L.gsn_g1_multiexp_multi_host(arr, len(devs), _ptr(out), _ptr(points), _ptr(scalars), points.shape[0])
+    if rc:
+        raise GsnError(rc, L.gsn_last_error().decode())
+    return out
+
+
 def device_count():
     L = _lib.load()
     c = C.c_int()

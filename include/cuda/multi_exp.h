@@ -5,8 +5,11 @@
 // ABI of libgpusnarks_b200.so:
 //     multiexp<fields::Scalar, fields::Scalar>      -> gsn_fp768_inner_product_host   (sum_i a[i] * mul[i] in the field)
 //     multiexp<fields::mnt4753_G1, fields::Scalar>  -> gsn_g1_multiexp_host           (sum_i mul[i] * a[i] on the curve, bucket method)
+//                                                      gsn_g1_multiexp_multi_host     (2^18 points and more, several GPUs visible)
 // Failures are reported by a std::runtime_error carrying gsn_last_error() (the reference prints and continues).
 #pragma once
+#include <algorithm>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -33,6 +36,19 @@ template <> struct multiexp_dispatch<fields::mnt4753_G1, fields::Scalar> {
     static fields::mnt4753_G1 run(std::vector<fields::mnt4753_G1> &a, std::vector<fields::Scalar> &mul) {
         if (a.size() != mul.size()) throw std::runtime_error("multiexp: vectors must have equal length");
         fields::mnt4753_G1 out;
+        // 2^18 points and more are cut into one slice per visible GPU (independent work; GSN_MULTI_DEVICES=1 switches it off)
+        int devices = 1;
+        if (a.size() >= ((size_t)1 << 18)) {
+            gsn_device_count(&devices);
+            if (const char *e = std::getenv("GSN_MULTI_DEVICES")) devices = std::min(devices, std::atoi(e));
+        }
+        if (devices > 1) {
+            std::vector<int> ids(devices);
+            for (int d = 0; d < devices; ++d) ids[d] = d;
+            check(gsn_g1_multiexp_multi_host(ids.data(), (unsigned)devices, reinterpret_cast<uint32_t *>(&out), reinterpret_cast<const uint32_t *>(a.data()),
+                                             reinterpret_cast<const uint32_t *>(mul.data()), a.size()), "gsn_g1_multiexp_multi_host");
+            return out;
+        }
         check(gsn_g1_multiexp_host(default_ctx(), reinterpret_cast<uint32_t *>(&out), reinterpret_cast<const uint32_t *>(a.data()),
                                    reinterpret_cast<const uint32_t *>(mul.data()), a.size()), "gsn_g1_multiexp_host");
         return out;

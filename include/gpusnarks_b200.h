@@ -235,6 +235,10 @@ int gsn_fp768_inner_product_host(gsn_ctx *ctx, uint32_t out[GSN_FP768_LIMBS], co
  * method (0 automatic, 1 the reference's own algorithm: one double-and-add per point then a tree reduction, 2 bucket
  * method) and the window width (0 automatic, else 2..16). */
 int gsn_g1_multiexp_host(gsn_ctx *ctx, uint32_t out[72], const uint32_t *points, const uint32_t *scalars, size_t n);
+/* the same over several devices of this process: the points are cut into n_devices contiguous slices, every device
+ * runs the bucket method on its slice (one host thread per device, contexts cached inside the library) and the partial
+ * sums are added on the host -- independent work, no exchange between the devices.  n_devices = 0: every visible device. */
+int gsn_g1_multiexp_multi_host(const int *devices, unsigned n_devices, uint32_t out[72], const uint32_t *points, const uint32_t *scalars, size_t n);
 int gsn_g1_multiexp_device(gsn_ctx *ctx, uint32_t *d_out, const uint32_t *d_points, const uint32_t *d_scalars, size_t n, void *stream);
 int gsn_g1_multiexp_device_ex(gsn_ctx *ctx, uint32_t *d_out, const uint32_t *d_points, const uint32_t *d_scalars, size_t n, unsigned method,
                               unsigned window_bits, void *stream);

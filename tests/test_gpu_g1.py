@@ -214,3 +214,23 @@ def test_split_buckets(fq_ctx):
             scaled[i::5, c] = np.array(pyref.to_limbs(v), dtype=np.uint32)
     out = fq_ctx.g1_multiexp(scaled, pyref.ints_to_array(ks), method="bucket", window_bits=4)
     assert _affine(out) == want
+
+
+def test_multiexp_sharded_over_the_visible_devices(fq_ctx):
+    """gsn_g1_multiexp_multi_host: one slice of the points per device (1, 2, ... 8 of them), partial sums added on the
+    host; an uneven split and a device list with one entry included.  Same point as the single-context call."""
+    import gpusnarks_b200 as g
+    from gpusnarks_b200.ntt import g1_multiexp_multi
+    rng = random.Random(61)
+    base = [g1ref.random_point(rng) for _ in range(7)]
+    n = 1003
+    pts = [base[i % 7] for i in range(n)]
+    ks = [rng.randrange(pyref.FR) for _ in range(n)]
+    packed, scal = _pack_points(pts), pyref.ints_to_array(ks)
+    want = g1ref.multiexp(base, [sum(ks[j::7]) for j in range(7)])
+    assert _affine(fq_ctx.g1_multiexp(packed, scal)) == want
+    assert _affine(g1_multiexp_multi(packed, scal)) == want                       # every visible device
+    assert _affine(g1_multiexp_multi(packed, scal, devices=[0])) == want
+    if g.device_count() >= 2:
+        assert _affine(g1_multiexp_multi(packed, scal, devices=[1, 0])) == want
+    assert _affine(g1_multiexp_multi(packed[:3], scal[:3], devices=[0] * 1)) == g1ref.multiexp(base[:3], ks[:3])

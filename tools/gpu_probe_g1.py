@@ -59,6 +59,16 @@ def main():
         res["host_call_ms"] = min(ms)
         res["host_call_all_ms"] = ms
         res["points_per_s_host_call"] = n / (min(ms) * 1e-3)
+        if g.device_count() > 1 and logn >= 16:
+            from gpusnarks_b200.ntt import g1_multiexp_multi
+            ms, ok = [], True
+            for rep in range(3):
+                t0 = time.perf_counter()
+                got = g1_multiexp_multi(pts, ks)     # one slice per visible device, partial sums added on the host
+                ms.append((time.perf_counter() - t0) * 1e3)
+            res["devices"] = g.device_count()
+            res["multi_host_call_ms"] = min(ms)
+            res["multi_equals_single"] = g1ref.from_projective_mont(*[pyref.from_limbs(got[c]) for c in range(3)]) == affine["bucket"]
         print(json.dumps({"log_n": logn, "points": n, **res}), flush=True)
     ctx.close()
 
