@@ -537,8 +537,8 @@ static int multi_staged_copy(gsn_multi *m, bool to_device, const MultiLayout &L,
             for (uint64_t r = nr * t / nt; r < nr * (t + 1) / nt; ++r)
                 for (uint64_t k = 0; k < l.runs; ++k) {
                     char *h = base + (r0 + r) * l.row_stride + k * l.run_stride, *b = bounce + r * l.row_bytes + k * l.run_bytes;
-                    if (gather) memcpy(b, h, l.run_bytes);
-                    else memcpy(h, b, l.run_bytes);
+                    if (gather) stream_copy(b, h, l.run_bytes);
+                    else stream_copy(h, b, l.run_bytes);
                 }
         });
     };

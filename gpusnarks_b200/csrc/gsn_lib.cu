@@ -831,15 +831,27 @@ static HostPool &host_pool(gsn_ctx *ctx) {
 
 // rows x width bytes between two pitched host buffers, rows split over the pool
 static void copy_rows(gsn_ctx *ctx, void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows) {
+    static const bool streaming = !(getenv("GSN_STREAM_COPY") && atoi(getenv("GSN_STREAM_COPY")) == 0);   // non-temporal stores (default on)
+    if (!streaming) {
+        host_pool(ctx).run([=](unsigned t, unsigned nt) {
+            if (dpitch == width && spitch == width) {
+                const size_t bytes = width * rows, per = ((bytes / nt) + 4095) & ~(size_t)4095, off = t * per;
+                if (off < bytes) memcpy((char *)dst + off, (const char *)src + off, std::min(per, bytes - off));
+                return;
+            }
+            for (size_t r = rows * t / nt; r < rows * (t + 1) / nt; ++r) memcpy((char *)dst + r * dpitch, (const char *)src + r * spitch, width);
+        });
+        return;
+    }
     host_pool(ctx).run([=](unsigned t, unsigned nt) {
         if (dpitch == width && spitch == width) {   // contiguous: split by bytes, page aligned
             const size_t bytes = width * rows, per = ((bytes / nt) + 4095) & ~(size_t)4095;
             const size_t off = t * per;
-            if (off < bytes) memcpy((char *)dst + off, (const char *)src + off, std::min(per, bytes - off));
+            if (off < bytes) stream_copy((char *)dst + off, (const char *)src + off, std::min(per, bytes - off));
             return;
         }
         const size_t r0 = rows * t / nt, r1 = rows * (t + 1) / nt;
-        for (size_t r = r0; r < r1; ++r) memcpy((char *)dst + r * dpitch, (const char *)src + r * spitch, width);
+        for (size_t r = r0; r < r1; ++r) stream_copy((char *)dst + r * dpitch, (const char *)src + r * spitch, width);
     });
 }
 

@@ -34,6 +34,20 @@ int main() {
         });
         CHECK(dst == want);
     }
+    // stream_copy: aligned large pieces (non-temporal stores), odd sizes and unaligned pointers (plain memcpy) all copy exactly
+    {
+        std::vector<unsigned char> raw_src(1 << 20), raw_dst(1 << 20);
+        for (size_t i = 0; i < raw_src.size(); ++i) raw_src[i] = (unsigned char)(i * 29 + 3);
+        unsigned char *s0 = raw_src.data() + ((16 - (uintptr_t)raw_src.data() % 16) % 16), *d0 = raw_dst.data() + ((16 - (uintptr_t)raw_dst.data() % 16) % 16);
+        for (size_t bytes : {(size_t)96, (size_t)4096, (size_t)12288, (size_t)12288 + 32, (size_t)100000, (size_t)100001})
+            for (size_t so : {(size_t)0, (size_t)16, (size_t)5})
+                for (size_t dof : {(size_t)0, (size_t)32, (size_t)7}) {
+                    memset(raw_dst.data(), 0, raw_dst.size());
+                    stream_copy(d0 + dof, s0 + so, bytes);
+                    CHECK(memcmp(d0 + dof, s0 + so, bytes) == 0);
+                    CHECK(d0[dof + bytes] == 0);
+                }
+    }
     printf("test_host_pool: ok\n");
     return 0;
 }
