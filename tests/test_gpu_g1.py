@@ -204,6 +204,8 @@ def test_split_buckets(fq_ctx):
     out = fq_ctx.g1_multiexp(packed, pyref.ints_to_array(ks), method="bucket", window_bits=4)
     want = g1ref.multiexp(base, [sum(ks[j::5]) for j in range(5)])
     assert _affine(out) == want
+    # the host entry point with the automatic window: 5.5 MB of pageable points go through the pinned bounce buffers
+    assert _affine(fq_ctx.g1_multiexp(packed, pyref.ints_to_array(ks))) == want
     # the same points in a non-affine projective representation (x l, y l, z l): the general addition path
     p = pyref.FQ
     lam = 0x1234567
