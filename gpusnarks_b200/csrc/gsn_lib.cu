@@ -1160,8 +1160,9 @@ static int g1_multiexp_pippenger(gsn_ctx *ctx, uint32_t *d_out, const uint32_t *
     CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr, (uint32_t *)nullptr,
                                        (int)pairs, 0, key_bits, st));
     // a bucket goes to the block-per-item kernels when it holds more than `limit` points: four times the average bucket
-    // (n / 2^(c-1) points; the window width is capped at 16 bits, so the average itself passes 128 from 2^22 points), at least 128
-    const uint32_t limit = (uint32_t)std::max<uint64_t>(128, 4 * ((uint64_t)n >> (c - 1)));
+    // (n / 2^(c-1) points; the window width is capped at 16 bits, so the average itself passes 128 from 2^22 points), at
+    // least 128 and at most 1024 -- no single thread walks more than that, however few buckets a narrow window leaves
+    const uint32_t limit = (uint32_t)std::min<uint64_t>(1024, std::max<uint64_t>(128, 4 * ((uint64_t)n >> (c - 1))));
     const uint32_t wparts = nb >= 8192 ? 4 : nb >= 2048 ? 2 : 1;   // blocks per window of the running-sum reduction
     // bounds of the heavy work list: every item but the split ones covers > limit points; a split bucket of s points has at most 2 s / 4096 parts
     const size_t split_cap = pairs / gsn::G1_SPLIT_POINTS + 2, slot_cap = 2 * split_cap + gsn::G1_MAX_PARTS, item_cap = pairs / limit + slot_cap + 2;

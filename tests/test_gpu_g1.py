@@ -218,6 +218,19 @@ def test_split_buckets(fq_ctx):
     assert _affine(out) == want
 
 
+def test_narrow_windows_many_points(fq_ctx):
+    """2-bit windows leave two buckets per window, each with about a quarter of ALL points: far above any per-thread
+    limit, so every bucket must go to the block-per-item kernels (a limit that only followed the average bucket size
+    would hand 7 500 points to one thread)"""
+    rng = random.Random(53)
+    base = [g1ref.random_point(rng) for _ in range(5)]
+    n = 30000
+    pts = [base[i % 5] for i in range(n)]
+    ks = [rng.randrange(1 << 16) for _ in range(n)]
+    out = fq_ctx.g1_multiexp(_pack_points(pts), pyref.ints_to_array(ks), method="bucket", window_bits=2)
+    assert _affine(out) == g1ref.multiexp(base, [sum(ks[j::5]) for j in range(5)])
+
+
 def test_multiexp_sharded_over_the_visible_devices(fq_ctx):
     """gsn_g1_multiexp_multi_host: one slice of the points per device (1, 2, ... 8 of them), partial sums added on the
     host; an uneven split and a device list with one entry included.  Same point as the single-context call."""
