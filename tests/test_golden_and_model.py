@@ -89,3 +89,11 @@ def test_device_product_models(p):
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import model_products
     assert model_products.self_check(p, cases=250, seed=3) <= 2
+
+
+def test_multiexp_bookkeeping_model():
+    """tools/model_msm.py: the bucket method's bookkeeping (signed window digits with carries, heavy / split work items
+    tiling a bucket exactly, the chunked running-sum window reduction over P blocks x T threads, Horner over the windows)
+    over the additive group of integers equals sum_i k_i * P_i, including full-width, zero and repeated scalars"""
+    import model_msm
+    assert model_msm.check()
